@@ -1,0 +1,122 @@
+// Shared device/host helpers for the coda_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+
+#include "../../include/coda_b200.h"
+
+#define CODA_WARP 32
+#define CODA_FULL 0xffffffffu
+
+// ---- error plumbing (thread-local message, C-ABI returns an int code) -----------------
+void coda_set_error(const char* fmt, ...);
+
+#define CODA_CHECK_ARG(cond, ...)                                   \
+  do {                                                              \
+    if (!(cond)) {                                                  \
+      coda_set_error(__VA_ARGS__);                                  \
+      return CODA_B200_EINVAL;                                      \
+    }                                                               \
+  } while (0)
+
+#define CODA_CUDA_OK(expr)                                                        \
+  do {                                                                            \
+    cudaError_t _e = (expr);                                                      \
+    if (_e != cudaSuccess) {                                                      \
+      coda_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),      \
+                     __FILE__, __LINE__);                                         \
+      return CODA_B200_ECUDA;                                                     \
+    }                                                                             \
+  } while (0)
+
+#define CODA_LAUNCH_OK(name)                                                      \
+  do {                                                                            \
+    cudaError_t _e = cudaGetLastError();                                          \
+    if (_e != cudaSuccess) {                                                      \
+      coda_set_error("launch of %s failed: %s", name, cudaGetErrorString(_e));    \
+      return CODA_B200_ECUDA;                                                     \
+    }                                                                             \
+  } while (0)
+
+static inline cudaStream_t as_stream(coda_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+int coda_sm_count();   // cached multiprocessor count of the current device
+
+// ---- warp primitives -----------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(CODA_FULL, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(CODA_FULL, v, o));
+  return v;
+}
+
+// (value, index) arg-max with "first index wins" on equal values (torch.argmax on CPU).
+__device__ __forceinline__ void warp_argmax(float& v, int& i) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float ov = __shfl_xor_sync(CODA_FULL, v, o);
+    int oi = __shfl_xor_sync(CODA_FULL, i, o);
+    if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+  }
+}
+
+// ---- entropy term, coda.py:254/276: f(m) = -max(m,1e-12) * log2(max(m,1e-12)) ----------
+__device__ __forceinline__ float ent_term(float m) {
+  float q = fmaxf(m, 1e-12f);
+  return -q * log2f(q);
+}
+
+// ---- fixed-point accumulation (order- and shard-count-independent sums) ---------------
+// Values in [0, 1] are scaled by 2^shift and summed as int64; the host picks shift so that
+// N_global * 2^shift < 2^62.
+__device__ __forceinline__ long long to_fx(float v, int shift) {
+  return __double2ll_rn(ldexp((double)v, shift));
+}
+__host__ __device__ __forceinline__ double from_fx(long long v, int shift) {
+  return ldexp((double)v, -shift);
+}
+
+// ---- 1-D bulk TMA (cp.async.bulk, SASS UBLKCP) + mbarrier -------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// global -> shared bulk copy; bytes % 16 == 0, both addresses 16-byte aligned.
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}

@@ -1,0 +1,236 @@
+// Per-item EIG assembly, candidate arg-max and the isclose tie scan.
+//
+//   eig_points    coda.py:278   eig[b] = H_before - sum_c pi_hat_xi[b,c] * H_after[b,c]
+//                 written as sum_c xi[b,c] * gain(b,c) with gain = H_before - H_after (sum_c xi = 1)
+//                 and gain(b,c) = gain0[c] for every class no model predicts (template pair z0).
+//                 coda.py:215-219/239 candidate set: unlabeled & non-unanimous, else all unlabeled.
+//   select_merge  coda.py:306, 309: global max with first-index-wins over per-shard partials
+//   ties          coda.py:307   torch.isclose(q, best, rtol=1e-8, atol=1e-8) evaluated in fp32
+//   device_pick   on-device stand-in for oracle(idx) + the tie rule "lowest index" (bench `value` loop)
+#include "common.cuh"
+
+struct Best {
+  float v;
+  long long i;
+};
+__device__ __forceinline__ void best_update(Best& b, float v, long long i) {
+  if (v > b.v || (v == b.v && i < b.i)) { b.v = v; b.i = i; }
+}
+__device__ __forceinline__ void best_warp(Best& b) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float ov = __shfl_xor_sync(CODA_FULL, b.v, o);
+    long long oi = __shfl_xor_sync(CODA_FULL, b.i, o);
+    best_update(b, ov, oi);
+  }
+}
+
+#define IDX_NONE 0x7fffffffffffffffLL
+
+// partial record per block: 5 x int64 {bits(vA), iA, cntA, bits(vB), iB}
+__global__ void __launch_bounds__(256) k_eig_points(const float* __restrict__ U, long long N, int C,
+                                                    const long long* __restrict__ ent_off,
+                                                    const int32_t* __restrict__ ent_pair,
+                                                    const uint16_t* __restrict__ ent_cls,
+                                                    const float* __restrict__ gain,
+                                                    const long long* __restrict__ cls_base,
+                                                    const uint8_t* __restrict__ labeled,
+                                                    const uint8_t* __restrict__ disagree, long long n_offset,
+                                                    float* __restrict__ eig, long long* __restrict__ partials,
+                                                    uint32_t* __restrict__ flags) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* g0 = reinterpret_cast<float*>(smem_raw);   // [C] gain of the "no model predicts c" template
+  __shared__ float sv[2][8];
+  __shared__ long long si[2][8];
+  __shared__ long long sc[8];
+  for (int c = threadIdx.x; c < C; c += blockDim.x) g0[c] = gain[cls_base[c]];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  Best bA{-INFINITY, IDX_NONE}, bB{-INFINITY, IDX_NONE};
+  long long cntA = 0;
+  uint32_t bad = 0;
+  for (long long n = (long long)blockIdx.x * 8 + warp; n < N; n += (long long)gridDim.x * 8) {
+    const float* urow = U + (size_t)n * C;
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += urow[c];
+    s = warp_sum(s);
+    const float den = fmaxf(s, 1e-12f);                              // coda.py:230
+    float e = 0.f;
+    for (int c = lane; c < C; c += 32) e = fmaf(urow[c] / den, g0[c], e);
+    const long long o0 = ent_off[n], o1 = ent_off[n + 1];
+    for (long long k = o0 + lane; k < o1; k += 32) {
+      const int c = ent_cls[k];
+      e = fmaf(urow[c] / den, gain[ent_pair[k]] - g0[c], e);
+    }
+    e = warp_sum(e);
+    if (lane == 0) {
+      eig[n] = e;
+      if (!isfinite(e)) bad |= CODA_B200_FLAG_NONFINITE_EIG;
+      if (!labeled[n]) {
+        best_update(bB, e, n_offset + n);
+        if (disagree[n]) {
+          best_update(bA, e, n_offset + n);
+          ++cntA;
+        }
+      }
+    }
+  }
+  if (lane == 0) {
+    sv[0][warp] = bA.v; si[0][warp] = bA.i; sv[1][warp] = bB.v; si[1][warp] = bB.i; sc[warp] = cntA;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    Best a{-INFINITY, IDX_NONE}, b{-INFINITY, IDX_NONE};
+    long long cn = 0;
+    for (int w = 0; w < 8; ++w) {
+      best_update(a, sv[0][w], si[0][w]);
+      best_update(b, sv[1][w], si[1][w]);
+      cn += sc[w];
+    }
+    long long* out = partials + (size_t)blockIdx.x * 5;
+    out[0] = (long long)__float_as_int(a.v); out[1] = a.i; out[2] = cn;
+    out[3] = (long long)__float_as_int(b.v); out[4] = b.i;
+  }
+  if (bad) atomicOr(flags, bad);
+}
+
+extern "C" int coda_b200_eig_blocks(int64_t N) {
+  long long want = (N + 7) / 8;
+  long long cap = (long long)coda_sm_count() * 8;
+  return (int)(want < cap ? (want < 1 ? 1 : want) : cap);
+}
+
+extern "C" int coda_b200_eig_points(const float* U, int64_t N, int C, const int64_t* ent_off, const int32_t* ent_pair,
+                                    const uint16_t* ent_cls, const float* gain, const int64_t* cls_base,
+                                    const uint8_t* labeled, const uint8_t* disagree, int64_t n_offset, float* eig,
+                                    int64_t* partials, uint32_t* flags, coda_stream_t stream) {
+  CODA_CHECK_ARG(U && ent_off && ent_pair && ent_cls && gain && cls_base && labeled && disagree && eig && partials && flags,
+                 "eig_points: null pointer");
+  size_t smem = (size_t)C * 4;
+  CODA_CHECK_ARG(smem <= 48 * 1024, "eig_points: C=%d too large", C);
+  int grid = coda_b200_eig_blocks(N);
+  k_eig_points<<<grid, 256, smem, as_stream(stream)>>>(U, N, C, reinterpret_cast<const long long*>(ent_off), ent_pair,
+                                                       ent_cls, gain, reinterpret_cast<const long long*>(cls_base),
+                                                       labeled, disagree, n_offset, eig,
+                                                       reinterpret_cast<long long*>(partials), flags);
+  CODA_LAUNCH_OK("k_eig_points");
+  return CODA_B200_OK;
+}
+
+// merge `nrec` partial records (from this shard's blocks, or one per rank after an all-gather)
+// into one record {bits(vA), iA, cntA, bits(vB), iB}.  nrec is small (<= a few thousand): one block.
+__global__ void __launch_bounds__(256) k_select_merge(const long long* __restrict__ recs, int nrec,
+                                                      long long* __restrict__ out) {
+  __shared__ float sv[2][8];
+  __shared__ long long si[2][8];
+  __shared__ long long sc[8];
+  Best a{-INFINITY, IDX_NONE}, b{-INFINITY, IDX_NONE};
+  long long cn = 0;
+  for (int r = threadIdx.x; r < nrec; r += blockDim.x) {
+    const long long* rec = recs + (size_t)r * 5;
+    best_update(a, __int_as_float((int)rec[0]), rec[1]);
+    best_update(b, __int_as_float((int)rec[3]), rec[4]);
+    cn += rec[2];
+  }
+  best_warp(a);
+  best_warp(b);
+  cn = warp_sum(cn);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { sv[0][warp] = a.v; si[0][warp] = a.i; sv[1][warp] = b.v; si[1][warp] = b.i; sc[warp] = cn; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    Best fa{-INFINITY, IDX_NONE}, fb{-INFINITY, IDX_NONE};
+    long long c = 0;
+    for (int w = 0; w < 8; ++w) {
+      best_update(fa, sv[0][w], si[0][w]);
+      best_update(fb, sv[1][w], si[1][w]);
+      c += sc[w];
+    }
+    out[0] = (long long)__float_as_int(fa.v); out[1] = fa.i; out[2] = c;
+    out[3] = (long long)__float_as_int(fb.v); out[4] = fb.i;
+  }
+}
+
+extern "C" int coda_b200_select_merge(const int64_t* recs, int nrec, int64_t* out, coda_stream_t stream) {
+  CODA_CHECK_ARG(recs && out && nrec >= 1, "select_merge: bad arguments");
+  k_select_merge<<<1, 256, 0, as_stream(stream)>>>(reinterpret_cast<const long long*>(recs), nrec,
+                                                   reinterpret_cast<long long*>(out));
+  CODA_LAUNCH_OK("k_select_merge");
+  return CODA_B200_OK;
+}
+
+// tie scan against the GLOBAL record `best` (after select_merge over all shards).
+// tie_hdr: {count, min tied global index}; tie_idx/tie_val hold up to `cap` entries (unordered).
+__global__ void __launch_bounds__(256) k_ties(const float* __restrict__ eig, long long N,
+                                              const uint8_t* __restrict__ labeled,
+                                              const uint8_t* __restrict__ disagree, long long n_offset,
+                                              const long long* __restrict__ best, int cap,
+                                              long long* __restrict__ tie_hdr, long long* __restrict__ tie_idx,
+                                              float* __restrict__ tie_val) {
+  const bool useA = best[2] > 0;                                      // coda.py:239 `or` fallback
+  const float bv = __int_as_float((int)(useA ? best[0] : best[3]));
+  const float tol = 1e-8f + fabsf(1e-8f * bv);                        // atol + rtol * |best| (fp32)
+  for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < N;
+       n += (long long)gridDim.x * blockDim.x) {
+    if (labeled[n]) continue;
+    if (useA && !disagree[n]) continue;
+    const float e = eig[n];
+    if (e == bv || fabsf(e - bv) <= tol) {
+      const long long g = n_offset + n;
+      unsigned long long k = atomicAdd(reinterpret_cast<unsigned long long*>(tie_hdr), 1ull);
+      atomicMin(tie_hdr + 1, g);
+      if (k < (unsigned long long)cap) {
+        tie_idx[k] = g;
+        tie_val[k] = e;
+      }
+    }
+  }
+}
+
+__global__ void k_ties_reset(long long* tie_hdr) {
+  tie_hdr[0] = 0;
+  tie_hdr[1] = IDX_NONE;
+}
+
+extern "C" int coda_b200_ties(const float* eig, int64_t N, const uint8_t* labeled, const uint8_t* disagree,
+                              int64_t n_offset, const int64_t* best, int cap, int64_t* tie_hdr, int64_t* tie_idx,
+                              float* tie_val, coda_stream_t stream) {
+  CODA_CHECK_ARG(eig && labeled && disagree && best && tie_hdr && tie_idx && tie_val, "ties: null pointer");
+  int grid = (int)min((long long)(N + 255) / 256, (long long)coda_sm_count() * 4);
+  if (grid < 1) grid = 1;
+  k_ties_reset<<<1, 1, 0, as_stream(stream)>>>(reinterpret_cast<long long*>(tie_hdr));
+  k_ties<<<grid, 256, 0, as_stream(stream)>>>(eig, N, labeled, disagree, n_offset,
+                                              reinterpret_cast<const long long*>(best), cap,
+                                              reinterpret_cast<long long*>(tie_hdr),
+                                              reinterpret_cast<long long*>(tie_idx), tie_val);
+  CODA_LAUNCH_OK("k_ties");
+  return CODA_B200_OK;
+}
+
+// device-resident stand-in for `oracle(idx)` (coda/oracle.py:23-24): picks the lowest tied global
+// index (tie_hdr[1], already min-reduced across shards by the caller), looks the label up in a
+// device-resident label vector and writes the {local idx or -1, class} record the update kernels read.
+__global__ void k_device_pick(const long long* __restrict__ tie_hdr, const long long* __restrict__ labels_global,
+                              long long n_offset, long long N, const float* __restrict__ eig,
+                              long long* __restrict__ sel, long long* __restrict__ hist_idx,
+                              float* __restrict__ hist_q, long long step) {
+  const long long g = tie_hdr[1];
+  const long long loc = g - n_offset;
+  const bool own = loc >= 0 && loc < N;
+  sel[0] = own ? loc : -1;
+  sel[1] = labels_global[g];
+  if (hist_idx) hist_idx[step] = g;
+  if (hist_q) hist_q[step] = own ? eig[loc] : 0.f;
+}
+
+extern "C" int coda_b200_device_pick(const int64_t* tie_hdr, const int64_t* labels_global, int64_t n_offset, int64_t N,
+                                     const float* eig, int64_t* sel, int64_t* hist_idx, float* hist_q, int64_t step,
+                                     coda_stream_t stream) {
+  CODA_CHECK_ARG(tie_hdr && labels_global && eig && sel, "device_pick: null pointer");
+  k_device_pick<<<1, 1, 0, as_stream(stream)>>>(reinterpret_cast<const long long*>(tie_hdr),
+                                                reinterpret_cast<const long long*>(labels_global), n_offset, N, eig,
+                                                reinterpret_cast<long long*>(sel),
+                                                reinterpret_cast<long long*>(hist_idx), hist_q, step);
+  CODA_LAUNCH_OK("k_device_pick");
+  return CODA_B200_OK;
+}

@@ -1,0 +1,429 @@
+// Slab-streaming kernels of the CODA hot path (HBM-bound passes over the (H, N, C) fp32
+// prediction slab) and the Bayesian posterior update.
+//
+//   scan_slab          reference coda.py:193-194 (ensemble mean -> pseudo labels),
+//                      coda.py:217-218, 263, 316 (per-model argmax), coda.py:215-219 (unanimity)
+//   confusion_accum    coda.py:42   (einsum 'nc,hnj->hcj' with one-hot pseudo labels)
+//   init_dirichlets    coda.py:43, 46-63, 196
+//   pi_full            coda.py:227-229 (einsum 'hcs,hns->hnc' summed over h, never materialised)
+//   pi_reduce          coda.py:230-233
+//   label_row / label_apply / pi_rank1   coda.py:316-319 (posterior update + marginal refresh,
+//                      restated as the rank-1 column update it algebraically is)
+#include "common.cuh"
+
+// ---------------------------------------------------------------------------------------
+// scan_slab: one pass over the slab.  CTA = tile of TN points, all H models.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_scan_slab(const float* __restrict__ preds, int H, long long N, int C,
+                                                   int TN, uint16_t* __restrict__ hard,
+                                                   int32_t* __restrict__ pseudo, uint8_t* __restrict__ disagree,
+                                                   uint32_t* __restrict__ flags) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* ens = reinterpret_cast<float*>(smem_raw);                       // [TN][C]
+  uint16_t* hard_t = reinterpret_cast<uint16_t*>(ens + (size_t)TN * C);  // [TN][H]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  const long long n0 = (long long)blockIdx.x * TN;
+  const int tn = (int)min((long long)TN, N - n0);
+  for (int i = threadIdx.x; i < TN * C; i += blockDim.x) ens[i] = 0.f;
+  __syncthreads();
+  uint32_t bad = 0;
+  for (int h = 0; h < H; ++h) {
+    const float* base = preds + ((size_t)h * N + n0) * C;
+    for (int p = warp; p < tn; p += nwarp) {
+      const float* row = base + (size_t)p * C;
+      float* erow = ens + (size_t)p * C;
+      float bv = -INFINITY;
+      int bi = 0x7fffffff;
+      for (int c = lane; c < C; c += 32) {
+        float v = __ldg(row + c);
+        if (!isfinite(v)) bad |= CODA_B200_FLAG_NONFINITE_INPUT;
+        if (v < 0.f || v > 1.0001f) bad |= CODA_B200_FLAG_RANGE_INPUT;
+        erow[c] += v;
+        if (v > bv) { bv = v; bi = c; }
+      }
+      warp_argmax(bv, bi);
+      if (lane == 0) hard_t[(size_t)p * H + h] = (uint16_t)(bi == 0x7fffffff ? 0 : bi);
+    }
+  }
+  __syncthreads();
+  // hard predictions: contiguous [tn][H] block
+  {
+    uint16_t* dst = hard + (size_t)n0 * H;
+    for (int i = threadIdx.x; i < tn * H; i += blockDim.x) dst[i] = hard_t[i];
+  }
+  const float fH = (float)H;
+  for (int p = warp; p < tn; p += nwarp) {
+    const float* erow = ens + (size_t)p * C;
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int c = lane; c < C; c += 32) {
+      float v = erow[c] / fH;   // util.py:14 mean(dim=0), then coda.py:194 argmax
+      if (v > bv) { bv = v; bi = c; }
+    }
+    warp_argmax(bv, bi);
+    const uint16_t* hr = hard_t + (size_t)p * H;
+    const uint16_t h0 = hr[0];
+    int diff = 0;
+    for (int h = lane; h < H; h += 32) diff |= (hr[h] != h0);
+    diff = __any_sync(CODA_FULL, diff);
+    if (lane == 0) {
+      pseudo[n0 + p] = (bi == 0x7fffffff ? 0 : bi);
+      disagree[n0 + p] = (uint8_t)(diff ? 1 : 0);
+    }
+  }
+  if (bad) atomicOr(flags, bad);
+}
+
+extern "C" int coda_b200_scan_slab(const float* preds, int H, int64_t N, int C, uint16_t* hard, int32_t* pseudo,
+                                   uint8_t* disagree, uint32_t* flags, coda_stream_t stream) {
+  CODA_CHECK_ARG(preds && hard && pseudo && disagree && flags, "scan_slab: null pointer");
+  CODA_CHECK_ARG(H >= 1 && C >= 2 && C <= 65535 && N >= 1, "scan_slab: bad dims H=%d N=%lld C=%d", H, (long long)N, C);
+  int TN = 32;
+  size_t need;
+  while (true) {
+    need = (size_t)TN * C * 4 + (size_t)TN * H * 2;
+    if (need <= 200 * 1024 || TN == 1) break;
+    TN >>= 1;
+  }
+  CODA_CHECK_ARG(need <= 200 * 1024, "scan_slab: H=%d C=%d does not fit shared memory", H, C);
+  CODA_CUDA_OK(cudaFuncSetAttribute(k_scan_slab, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+  long long grid = (N + TN - 1) / TN;
+  k_scan_slab<<<(unsigned)grid, 256, need, as_stream(stream)>>>(preds, H, N, C, TN, hard, pseudo, disagree, flags);
+  CODA_LAUNCH_OK("k_scan_slab");
+  return CODA_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// confusion_accum: conf_fx[h][pseudo_n][j] += fx(preds[h][n][j]); int64 fixed point so the
+// result does not depend on summation order or on how N is sharded across GPUs.
+// grid = (chunks, H).  Shared-memory table when C*C*8 fits, global atomics otherwise.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_confusion_accum(const float* __restrict__ preds,
+                                                         const int32_t* __restrict__ pseudo, int H, long long N,
+                                                         int C, int shift, long long chunk, int use_smem,
+                                                         unsigned long long* __restrict__ conf_fx) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned long long* tab = reinterpret_cast<unsigned long long*>(smem_raw);  // [C][C]
+  const int h = blockIdx.y;
+  const long long n_lo = (long long)blockIdx.x * chunk;
+  const long long n_hi = min(N, n_lo + chunk);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  unsigned long long* gtab = conf_fx + (size_t)h * C * C;
+  if (use_smem) {
+    for (int i = threadIdx.x; i < C * C; i += blockDim.x) tab[i] = 0ull;
+    __syncthreads();
+  }
+  unsigned long long* dst_tab = use_smem ? tab : gtab;
+  for (long long n = n_lo + warp; n < n_hi; n += nwarp) {
+    const int y = pseudo[n];
+    const float* row = preds + ((size_t)h * N + n) * C;
+    unsigned long long* dst = dst_tab + (size_t)y * C;
+    for (int j = lane; j < C; j += 32) {
+      long long v = to_fx(__ldg(row + j), shift);
+      if (v != 0) atomicAdd(dst + j, (unsigned long long)v);
+    }
+  }
+  if (use_smem) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < C * C; i += blockDim.x) {
+      unsigned long long v = tab[i];
+      if (v) atomicAdd(gtab + i, v);
+    }
+  }
+}
+
+extern "C" int coda_b200_confusion_accum(const float* preds, const int32_t* pseudo, int H, int64_t N, int C,
+                                         int fx_shift, int64_t* conf_fx, coda_stream_t stream) {
+  CODA_CHECK_ARG(preds && pseudo && conf_fx, "confusion_accum: null pointer");
+  CODA_CHECK_ARG(fx_shift >= 8 && fx_shift <= 46, "confusion_accum: bad fx_shift %d", fx_shift);
+  size_t tab = (size_t)C * C * 8;
+  int use_smem = tab <= 160 * 1024;
+  size_t smem = use_smem ? tab : 0;
+  if (use_smem) CODA_CUDA_OK(cudaFuncSetAttribute(k_confusion_accum, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  long long chunk = 8192;
+  long long chunks = (N + chunk - 1) / chunk;
+  dim3 grid((unsigned)chunks, (unsigned)H);
+  k_confusion_accum<<<grid, 256, smem, as_stream(stream)>>>(preds, pseudo, H, N, C, fx_shift, chunk, use_smem,
+                                                           reinterpret_cast<unsigned long long*>(conf_fx));
+  CODA_LAUNCH_OK("k_confusion_accum");
+  return CODA_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// init_dirichlets: D = multiplier * (base + prior_strength * conf / max(rowsum, 1e-6))
+// one warp per (h, c) row.
+// ---------------------------------------------------------------------------------------
+__global__ void k_init_dirichlets(const long long* __restrict__ conf_fx, int H, int C, int shift,
+                                  float prior_strength, float multiplier, int uniform_prior,
+                                  float* __restrict__ D) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= (long long)H * C) return;
+  const int c = (int)(row % C);
+  const long long* src = conf_fx + row * C;
+  float rs = 0.f;
+  for (int j = lane; j < C; j += 32) rs += (float)from_fx(src[j], shift);
+  rs = warp_sum(rs);
+  rs = fmaxf(rs, 1e-6f);                                        // coda.py:43 clamp_min(1e-6)
+  const float off = uniform_prior ? (float)(2.0 / C) : (float)(1.0 / (C - 1));   // coda.py:53, 57
+  for (int j = lane; j < C; j += 32) {
+    float conf = (float)from_fx(src[j], shift) / rs;
+    float base = (!uniform_prior && j == c) ? 1.0f : off;       // coda.py:60 fill_diagonal_(1.0)
+    D[row * C + j] = multiplier * (base + prior_strength * conf);  // coda.py:63, 196
+  }
+}
+
+extern "C" int coda_b200_init_dirichlets(const int64_t* conf_fx, int H, int C, int fx_shift, double prior_strength,
+                                         double multiplier, int uniform_prior, float* D, coda_stream_t stream) {
+  CODA_CHECK_ARG(conf_fx && D, "init_dirichlets: null pointer");
+  long long rows = (long long)H * C;
+  int wpb = 8;
+  k_init_dirichlets<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, as_stream(stream)>>>(
+      reinterpret_cast<const long long*>(conf_fx), H, C, fx_shift, (float)prior_strength, (float)multiplier,
+      uniform_prior, D);
+  CODA_LAUNCH_OK("k_init_dirichlets");
+  return CODA_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// pi_full: U[n][c] = sum_h sum_s D[h][c][s] * preds[h][n][s]   (fp32 SIMT GEMM, K = H*C)
+// CTA: 64 points x (up to 128 classes per pass); thread (pg, cg) owns 4 points x 8 classes.
+// ---------------------------------------------------------------------------------------
+#define PF_TN 64
+#define PF_TC 128
+#define PF_SK 32
+__global__ void __launch_bounds__(256) k_pi_full(const float* __restrict__ preds, const float* __restrict__ D,
+                                                 int H, long long N, int C, float* __restrict__ U) {
+  __shared__ float As[PF_TN][PF_SK + 1];
+  __shared__ float Bs[PF_TC][PF_SK + 1];
+  const int tid = threadIdx.x;
+  const int pg = tid >> 4, cg = tid & 15;
+  const long long n0 = (long long)blockIdx.x * PF_TN;
+  for (int c0 = 0; c0 < C; c0 += PF_TC) {
+    float acc[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[i][k] = 0.f;
+    for (int h = 0; h < H; ++h) {
+      const float* Ah = preds + ((size_t)h * N) * C;
+      const float* Dh = D + ((size_t)h * C) * C;
+      for (int s0 = 0; s0 < C; s0 += PF_SK) {
+        __syncthreads();
+        for (int e = tid; e < PF_TN * PF_SK; e += 256) {
+          int r = e >> 5, col = e & 31;
+          long long n = n0 + r;
+          int s = s0 + col;
+          As[r][col] = (n < N && s < C) ? __ldg(Ah + (size_t)n * C + s) : 0.f;
+        }
+        for (int e = tid; e < PF_TC * PF_SK; e += 256) {
+          int r = e >> 5, col = e & 31;
+          int c = c0 + r, s = s0 + col;
+          Bs[r][col] = (c < C && s < C) ? __ldg(Dh + (size_t)c * C + s) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int s = 0; s < PF_SK; ++s) {
+          float a[4], b[8];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) a[i] = As[pg * 4 + i][s];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) b[k] = Bs[cg + 16 * k][s];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[i][k] = fmaf(a[i], b[k], acc[i][k]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      long long n = n0 + pg * 4 + i;
+      if (n >= N) continue;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        int c = c0 + cg + 16 * k;
+        if (c < C) U[(size_t)n * C + c] = acc[i][k];
+      }
+    }
+  }
+}
+
+extern "C" int coda_b200_pi_full(const float* preds, const float* D, int H, int64_t N, int C, float* U,
+                                 coda_stream_t stream) {
+  CODA_CHECK_ARG(preds && D && U, "pi_full: null pointer");
+  long long grid = (N + PF_TN - 1) / PF_TN;
+  k_pi_full<<<(unsigned)grid, 256, 0, as_stream(stream)>>>(preds, D, H, N, C, U);
+  CODA_LAUNCH_OK("k_pi_full");
+  return CODA_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// shared tail of pi_reduce / pi_rank1: one warp normalises one row of U and accumulates the
+// per-class column sums of pi_hat_xi (fixed point) into a warp-private shared-memory vector.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void row_accumulate(float* __restrict__ urow, int C, int lane, int shift, int t,
+                                               float delta_t, float* __restrict__ xi_out,
+                                               long long* __restrict__ wacc, uint32_t& bad) {
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    float u = urow[c];
+    if (c == t) {
+      u += delta_t;
+      urow[c] = u;
+    }
+    s += u;
+  }
+  s = warp_sum(s);
+  if (!isfinite(s)) bad |= CODA_B200_FLAG_NONFINITE_PI;
+  const float den = fmaxf(s, 1e-12f);                               // coda.py:230 clamp_(min=1e-12)
+  for (int c = lane; c < C; c += 32) {
+    float xi = urow[c] / den;   // column t was rewritten above by this same lane
+
+    if (xi_out) xi_out[c] = xi;
+    wacc[c] += to_fx(xi, shift);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_pi_reduce(float* __restrict__ U, long long N, int C, int shift,
+                                                   float* __restrict__ xi_out,
+                                                   unsigned long long* __restrict__ pisum_fx,
+                                                   uint32_t* __restrict__ flags) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  long long* wacc_all = reinterpret_cast<long long*>(smem_raw);       // [nwarp][C]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  long long* wacc = wacc_all + (size_t)warp * C;
+  for (int c = lane; c < C; c += 32) wacc[c] = 0;
+  __syncwarp();
+  uint32_t bad = 0;
+  for (long long n = (long long)blockIdx.x * nwarp + warp; n < N; n += (long long)gridDim.x * nwarp)
+    row_accumulate(U + (size_t)n * C, C, lane, shift, -1, 0.f, xi_out ? xi_out + (size_t)n * C : nullptr, wacc, bad);
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    long long s = 0;
+    for (int w = 0; w < nwarp; ++w) s += wacc_all[(size_t)w * C + c];
+    if (s) atomicAdd(pisum_fx + c, (unsigned long long)s);
+  }
+  if (bad) atomicOr(flags, bad);
+}
+
+extern "C" int coda_b200_pi_reduce(float* U, int64_t N, int C, int fx_shift, float* xi_out, int64_t* pisum_fx,
+                                   uint32_t* flags, coda_stream_t stream) {
+  CODA_CHECK_ARG(U && pisum_fx && flags, "pi_reduce: null pointer");
+  size_t smem = (size_t)8 * C * 8;
+  CODA_CHECK_ARG(smem <= 200 * 1024, "pi_reduce: C=%d too large", C);
+  CODA_CUDA_OK(cudaFuncSetAttribute(k_pi_reduce, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  long long want = (N + 7) / 8;
+  int grid = (int)min(want, (long long)coda_sm_count() * 8);
+  k_pi_reduce<<<grid, 256, smem, as_stream(stream)>>>(U, N, C, fx_shift, xi_out,
+                                                      reinterpret_cast<unsigned long long*>(pisum_fx), flags);
+  CODA_LAUNCH_OK("k_pi_reduce");
+  return CODA_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// posterior update (coda.py:316-317) and the marginal refresh it triggers (coda.py:319),
+// restated:  D[h, t, j_h] += lr   with j_h = p_h(idx)   changes only row t of every D[h], so
+//   U[n, t] += lr * sum_h preds[h, n, j_h]      and every other column of U is untouched.
+// label_row   : owner of idx publishes j_h (jvec) and marks the point labeled
+// label_apply : every rank applies the increment to its replica of D
+// pi_rank1    : gathers one float per (h, n) (one 32 B sector each), updates column t of U,
+//               renormalises rows on the fly and re-accumulates sum_n pi_hat_xi[n, :]
+// ---------------------------------------------------------------------------------------
+__global__ void k_label_row(const uint16_t* __restrict__ hard, int H, long long N, const long long* __restrict__ sel,
+                            int32_t* __restrict__ jvec, uint8_t* __restrict__ labeled) {
+  const long long idx = sel[0];
+  if (idx < 0 || idx >= N) return;   // not owned by this shard
+  for (int h = threadIdx.x; h < H; h += blockDim.x) jvec[h] = hard[(size_t)idx * H + h];
+  if (threadIdx.x == 0) labeled[idx] = 1;
+}
+
+__global__ void k_label_apply(float* __restrict__ D, int H, int C, const long long* __restrict__ sel,
+                              const int32_t* __restrict__ jvec, float lr) {
+  const int t = (int)sel[1];
+  if (t < 0 || t >= C) return;
+  for (int h = threadIdx.x; h < H; h += blockDim.x) {
+    int j = jvec[h];
+    D[((size_t)h * C + t) * C + j] += lr;                          // coda.py:317
+  }
+}
+
+extern "C" int coda_b200_label_row(const uint16_t* hard, int H, int64_t N, const int64_t* sel, int32_t* jvec,
+                                   uint8_t* labeled, coda_stream_t stream) {
+  CODA_CHECK_ARG(hard && sel && jvec && labeled, "label_row: null pointer");
+  k_label_row<<<1, 256, 0, as_stream(stream)>>>(hard, H, N, reinterpret_cast<const long long*>(sel), jvec, labeled);
+  CODA_LAUNCH_OK("k_label_row");
+  return CODA_B200_OK;
+}
+
+extern "C" int coda_b200_label_apply(float* D, int H, int C, const int64_t* sel, const int32_t* jvec, double lr,
+                                     coda_stream_t stream) {
+  CODA_CHECK_ARG(D && sel && jvec, "label_apply: null pointer");
+  k_label_apply<<<1, 256, 0, as_stream(stream)>>>(D, H, C, reinterpret_cast<const long long*>(sel), jvec, (float)lr);
+  CODA_LAUNCH_OK("k_label_apply");
+  return CODA_B200_OK;
+}
+
+#define R1_TN 256
+__global__ void __launch_bounds__(256) k_pi_rank1(const float* __restrict__ preds, int H, long long N, int C,
+                                                  const long long* __restrict__ sel,
+                                                  const int32_t* __restrict__ jvec, float lr, int shift,
+                                                  float* __restrict__ U, unsigned long long* __restrict__ pisum_fx,
+                                                  uint32_t* __restrict__ flags) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  long long* wacc_all = reinterpret_cast<long long*>(smem_raw);                 // [8][C]
+  float* delta = reinterpret_cast<float*>(wacc_all + (size_t)8 * C);            // [R1_TN]
+  int32_t* js = reinterpret_cast<int32_t*>(delta + R1_TN);                      // [H]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = (int)sel[1];
+  long long* wacc = wacc_all + (size_t)warp * C;
+  for (int c = lane; c < C; c += 32) wacc[c] = 0;
+  for (int h = threadIdx.x; h < H; h += blockDim.x) js[h] = jvec[h];
+  __syncthreads();
+  uint32_t bad = 0;
+  const size_t hstride = (size_t)N * C;
+  for (long long n0 = (long long)blockIdx.x * R1_TN; n0 < N; n0 += (long long)gridDim.x * R1_TN) {
+    const long long n = n0 + threadIdx.x;
+    float d = 0.f;
+    if (n < N) {
+      const float* p = preds + (size_t)n * C;
+      int h = 0;
+      for (; h + 8 <= H; h += 8) {
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = __ldg(p + (size_t)(h + k) * hstride + js[h + k]);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) d += v[k];
+      }
+      for (; h < H; ++h) d += __ldg(p + (size_t)h * hstride + js[h]);
+    }
+    delta[threadIdx.x] = lr * d;
+    __syncthreads();
+    const int rows = (int)min((long long)R1_TN, N - n0);
+    for (int r = warp; r < rows; r += 8)
+      row_accumulate(U + (size_t)(n0 + r) * C, C, lane, shift, t, delta[r], nullptr, wacc, bad);
+    __syncthreads();
+  }
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    long long s = 0;
+    for (int w = 0; w < 8; ++w) s += wacc_all[(size_t)w * C + c];
+    if (s) atomicAdd(pisum_fx + c, (unsigned long long)s);
+  }
+  if (bad) atomicOr(flags, bad);
+}
+
+extern "C" int coda_b200_pi_rank1(const float* preds, int H, int64_t N, int C, const int64_t* sel,
+                                  const int32_t* jvec, double lr, int fx_shift, float* U, int64_t* pisum_fx,
+                                  uint32_t* flags, coda_stream_t stream) {
+  CODA_CHECK_ARG(preds && sel && jvec && U && pisum_fx && flags, "pi_rank1: null pointer");
+  size_t smem = (size_t)8 * C * 8 + R1_TN * 4 + (size_t)H * 4;
+  CODA_CHECK_ARG(smem <= 200 * 1024, "pi_rank1: C=%d H=%d too large", C, H);
+  CODA_CUDA_OK(cudaFuncSetAttribute(k_pi_rank1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  long long want = (N + R1_TN - 1) / R1_TN;
+  int grid = (int)min(want, (long long)coda_sm_count() * 8);
+  k_pi_rank1<<<grid, 256, smem, as_stream(stream)>>>(preds, H, N, C, reinterpret_cast<const long long*>(sel), jvec,
+                                                     (float)lr, fx_shift, U,
+                                                     reinterpret_cast<unsigned long long*>(pisum_fx), flags);
+  CODA_LAUNCH_OK("k_pi_rank1");
+  return CODA_B200_OK;
+}

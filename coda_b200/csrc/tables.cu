@@ -1,0 +1,253 @@
+// Beta quadrature tables and the P(best) mixture.
+//
+// The reference (coda.py:77-119) evaluates, for every hypothetical (item b, class c), the
+// pdf / cumulative-trapezoid cdf of H Beta distributions on a 256-node grid.  Only three
+// distinct Betas exist per (model h, class c):  before=(a, b), miss=(a, b+w), hit=(a+w, b)
+// (coda.py:150-168), so they are tabulated once per class and the per-item work reduces to
+//
+//   prob_h(b, c) = sum_x G_{z_h}[c][x][h] * D_{b,c}(x),      D_{b,c}(x) = exp(sum_{h in Z} dL[c][h][x])
+//
+// with Z = {h : p_h(b) = c}, z_h = [h in Z] and
+//   dL[c][h][x]  = L_hit - L_miss                       (L = log(max(cdf, 1e-30)), coda.py:104)
+//   G0[c][x][h]  = wq[x] * pdf_miss[h][x] * exp(clamp(S0_c[x] - L_miss[h][x], -80, 80))
+//   G1[c][x][h]  = wq[x] * pdf_hit [h][x] * exp(clamp(S0_c[x] - L_hit [h][x], -80, 80))
+//   S0_c[x]      = sum_h L_miss[h][x]                   (coda.py:107 leave-one-out product)
+//   wq           = trapezoid weights of the fp32 grid   (coda.py:111 torch.trapz)
+// The +-80 clamp of coda.py:107 is applied to the class-level factor; it differs from the
+// reference's per-item clamp only where the integrand is below e^-80.
+// PB[c][h] is the "before" row P(h best | class c) (coda.py:245-251, 325-332), normalised.
+//
+// Tables are built in fp64 from fp32 inputs and rounded to fp32 once.
+#include "common.cuh"
+
+#define TP_ 256   // quadrature nodes == threads per block in the table kernels
+
+__device__ __forceinline__ double block_scan_incl(double v, double* wsum /*[8]*/) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    double t = __shfl_up_sync(CODA_FULL, v, o);
+    if (lane >= o) v += t;
+  }
+  if (lane == 31) wsum[warp] = v;
+  __syncthreads();
+  double off = 0.0;
+  for (int w = 0; w < warp; ++w) off += wsum[w];
+  __syncthreads();
+  return v + off;
+}
+
+// grid = (H, ncls); block = 256 threads, one per node.
+__global__ void __launch_bounds__(TP_) k_beta_nodes(const float* __restrict__ D, const float* __restrict__ grid_x,
+                                                    int H, int C, int cls_lo, float w,
+                                                    const long long* __restrict__ sel,
+                                                    double* __restrict__ pdf_s, double* __restrict__ L_s,
+                                                    uint32_t* __restrict__ flags) {
+  if (sel) cls_lo = (int)sel[1];   // device-resident class (host-free loop)
+  __shared__ double red[8];
+  __shared__ double wsum[8];
+  __shared__ double pdf_sh[TP_];
+  const int h = blockIdx.x, ci = blockIdx.y, c = cls_lo + ci, x = threadIdx.x;
+  const int ncls = gridDim.y;
+  const float* drow = D + ((size_t)h * C + c) * C;
+  // rowsum (coda.py:24): accumulate in double, round once to fp32
+  double part = 0.0;
+  for (int j = x; j < C; j += TP_) part += (double)drow[j];
+  part = warp_sum(part);
+  if ((x & 31) == 0) red[x >> 5] = part;
+  __syncthreads();
+  double rs = 0.0;
+  for (int k = 0; k < 8; ++k) rs += red[k];
+  const float alpha = drow[c];
+  const float beta = (float)rs - alpha;                          // coda.py:24
+  const float xf = grid_x[x];
+  const double lx = log((double)xf);
+  const double l1x = log((double)(1.0f - xf));                    // fp32 (1 - x) as the reference forms it
+  const float dxf = x > 0 ? (xf - grid_x[x - 1]) : 0.f;           // coda.py:100 (fp32 difference)
+  uint32_t bad = 0;
+  for (int v = 0; v < 3; ++v) {
+    const float a = alpha + (v == 2 ? w : 0.f);                   // coda.py:165
+    const float b = beta + (v == 1 ? w : 0.f);                    // coda.py:166
+    // torch.distributions.Dirichlet.log_prob (dirichlet.py:90-97) on [x, 1-x] with conc [a, b]
+    const double am1 = (double)(a - 1.0f), bm1 = (double)(b - 1.0f);
+    const double t1 = (am1 == 0.0) ? 0.0 : am1 * lx;              // xlogy(0, .) = 0
+    const double t2 = (bm1 == 0.0) ? 0.0 : bm1 * l1x;
+    const double lp = (t1 + t2) + lgamma((double)(a + b)) - (lgamma((double)a) + lgamma((double)b));
+    const double pdf = exp(lp);
+    if (!isfinite(pdf) || !(a > 0.f) || !(b > 0.f)) bad |= CODA_B200_FLAG_NONFINITE_TABLE;
+    __syncthreads();
+    pdf_sh[x] = pdf;
+    __syncthreads();
+    const double inc = x > 0 ? 0.5 * (pdf + pdf_sh[x - 1]) * (double)dxf : 0.0;   // coda.py:101
+    const double cdf = block_scan_incl(inc, wsum);
+    const double L = log(fmax(cdf, (double)1e-30f));              // coda.py:104
+    const size_t o = (((size_t)v * ncls + ci) * H + h) * TP_ + x;
+    pdf_s[o] = pdf;
+    L_s[o] = L;
+  }
+  if (bad) atomicOr(flags, bad);
+}
+
+// grid = (ncls); block = 256 threads, one per node.  Writes dL, G0T, G1T, PB for the class.
+__global__ void __launch_bounds__(TP_) k_beta_combine(const double* __restrict__ pdf_s, const double* __restrict__ L_s,
+                                                      const float* __restrict__ grid_x, int H, int Hp, int cls_lo,
+                                                      const long long* __restrict__ sel, float* __restrict__ dL, float* __restrict__ G0T,
+                                                      float* __restrict__ G1T, float* __restrict__ PB,
+                                                      uint32_t* __restrict__ flags) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  if (sel) cls_lo = (int)sel[1];
+  double* part = reinterpret_cast<double*>(smem_raw);   // [8][Hp]  per-warp partial sums of the before-integrand
+  __shared__ double red[8];
+  const int ci = blockIdx.x, c = cls_lo + ci, x = threadIdx.x, ncls = gridDim.x;
+  const int lane = x & 31, warp = x >> 5;
+  const size_t plane = (size_t)ncls * H * TP_;
+  const double* Lb = L_s + 0 * plane + (size_t)ci * H * TP_;
+  const double* Lm = L_s + 1 * plane + (size_t)ci * H * TP_;
+  const double* Lh = L_s + 2 * plane + (size_t)ci * H * TP_;
+  const double* pb = pdf_s + 0 * plane + (size_t)ci * H * TP_;
+  const double* pm = pdf_s + 1 * plane + (size_t)ci * H * TP_;
+  const double* ph = pdf_s + 2 * plane + (size_t)ci * H * TP_;
+  // trapezoid weight of node x from the fp32 grid differences (coda.py:111)
+  const float xf = grid_x[x];
+  const float dl_ = x > 0 ? xf - grid_x[x - 1] : 0.f;
+  const float dr_ = x < TP_ - 1 ? grid_x[x + 1] - xf : 0.f;
+  const double wq = 0.5 * ((double)dl_ + (double)dr_);
+  double S0 = 0.0, SB = 0.0;
+  for (int h = 0; h < H; ++h) {
+    S0 += Lm[(size_t)h * TP_ + x];
+    SB += Lb[(size_t)h * TP_ + x];
+  }
+  uint32_t bad = 0;
+  for (int h = 0; h < H; ++h) {
+    const size_t o = (size_t)h * TP_ + x;
+    const double lm = Lm[o], lh = Lh[o], lb = Lb[o];
+    const double g0 = wq * pm[o] * exp(fmin(fmax(S0 - lm, -80.0), 80.0));
+    const double g1 = wq * ph[o] * exp(fmin(fmax(S0 - lh, -80.0), 80.0));
+    double ib = wq * pb[o] * exp(fmin(fmax(SB - lb, -80.0), 80.0));
+    const float g0f = (float)g0, g1f = (float)g1;
+    if (!isfinite(g0f) || !isfinite(g1f) || !isfinite(ib)) bad |= CODA_B200_FLAG_NONFINITE_TABLE;
+    dL[((size_t)c * H + h) * TP_ + x] = (float)(lh - lm);
+    G0T[((size_t)c * TP_ + x) * Hp + h] = g0f;
+    G1T[((size_t)c * TP_ + x) * Hp + h] = g1f;
+    ib = warp_sum(ib);
+    if (lane == 0) part[(size_t)warp * Hp + h] = ib;
+  }
+  __syncthreads();
+  // PB row: sum the 8 warp partials in fixed order, normalise over h (coda.py:114)
+  double tot = 0.0;
+  for (int h = x; h < H; h += TP_) {
+    double s = 0.0;
+    for (int w8 = 0; w8 < 8; ++w8) s += part[(size_t)w8 * Hp + h];
+    part[h] = s;   // warp-0 slot reused: only this thread touches column h
+    tot += s;
+  }
+  tot = warp_sum(tot);
+  if (lane == 0) red[warp] = tot;
+  __syncthreads();
+  double total = 0.0;
+  for (int k = 0; k < 8; ++k) total += red[k];
+  if (!isfinite(total)) bad |= CODA_B200_FLAG_NONFINITE_TABLE;
+  total = fmax(total, (double)1e-30f);
+  for (int h = x; h < Hp; h += TP_) PB[(size_t)c * Hp + h] = h < H ? (float)(part[h] / total) : 0.f;
+  if (bad) atomicOr(flags, bad);
+}
+
+extern "C" size_t coda_b200_tables_scratch_bytes(int H, int ncls) {
+  return (size_t)2 * 3 * ncls * H * TP_ * sizeof(double);
+}
+
+extern "C" int coda_b200_beta_tables(const float* D, const float* grid_x, int H, int C, int P, double hyp_w,
+                                     int cls_lo, int cls_hi, const int64_t* sel, void* scratch, float* dL,
+                                     float* G0T, float* G1T, float* PB, uint32_t* flags, coda_stream_t stream) {
+  CODA_CHECK_ARG(D && grid_x && scratch && dL && G0T && G1T && PB && flags, "beta_tables: null pointer");
+  CODA_CHECK_ARG(P == TP_, "beta_tables: P must be %d", TP_);
+  if (sel) { cls_lo = 0; cls_hi = 1; }   // one class, index read from sel[1] on the device
+  CODA_CHECK_ARG(0 <= cls_lo && cls_lo < cls_hi && cls_hi <= C, "beta_tables: bad class range [%d,%d)", cls_lo, cls_hi);
+  const int ncls = cls_hi - cls_lo;
+  const long long* seld = reinterpret_cast<const long long*>(sel);
+  const int Hp = (H + 31) / 32 * 32;
+  double* pdf_s = reinterpret_cast<double*>(scratch);
+  double* L_s = pdf_s + (size_t)3 * ncls * H * TP_;
+  dim3 g1((unsigned)H, (unsigned)ncls);
+  k_beta_nodes<<<g1, TP_, 0, as_stream(stream)>>>(D, grid_x, H, C, cls_lo, (float)hyp_w, seld, pdf_s, L_s, flags);
+  CODA_LAUNCH_OK("k_beta_nodes");
+  size_t smem = (size_t)8 * Hp * sizeof(double);
+  CODA_CHECK_ARG(smem <= 200 * 1024, "beta_tables: H=%d too large", H);
+  CODA_CUDA_OK(cudaFuncSetAttribute(k_beta_combine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_beta_combine<<<ncls, TP_, smem, as_stream(stream)>>>(pdf_s, L_s, grid_x, H, Hp, cls_lo, seld, dL, G0T, G1T, PB, flags);
+  CODA_LAUNCH_OK("k_beta_combine");
+  return CODA_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// mixture: pi_hat = normalise(sum_n pi_hat_xi) (coda.py:232-233), m0[h] = sum_c pi_hat[c] PB[c][h]
+// (coda.py:253 == coda.py:145, the P(best) vector), H_before (coda.py:254) and argmax (coda.py:346).
+// single block.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_mixture(const long long* __restrict__ pisum_fx, const float* __restrict__ PB,
+                                                 int H, int Hp, int C, float* __restrict__ pi_hat,
+                                                 float* __restrict__ m0, float* __restrict__ hb_out,
+                                                 long long* __restrict__ best_out, uint32_t* __restrict__ flags) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* pis = reinterpret_cast<float*>(smem_raw);   // [C]
+  __shared__ float redv[8];
+  __shared__ int redi[8];
+  __shared__ long long tot_s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+    long long t = 0;
+    for (int c = 0; c < C; ++c) t += pisum_fx[c];
+    tot_s = t;
+  }
+  __syncthreads();
+  const double tot = (double)tot_s;
+  for (int c = tid; c < C; c += 256) {
+    float p = (float)((double)pisum_fx[c] / tot);
+    pis[c] = p;
+    pi_hat[c] = p;
+  }
+  __syncthreads();
+  float ent = 0.f, bv = -INFINITY;
+  int bi = 0x7fffffff;
+  uint32_t bad = 0;
+  for (int h = tid; h < Hp; h += 256) {
+    float m = 0.f;
+    if (h < H) {
+      for (int c = 0; c < C; ++c) m = fmaf(pis[c], PB[(size_t)c * Hp + h], m);
+      if (!isfinite(m)) bad |= CODA_B200_FLAG_NONFINITE_PBEST;
+      ent += ent_term(m);
+      if (m > bv) { bv = m; bi = h; }
+    }
+    m0[h] = m;
+  }
+  ent = warp_sum(ent);
+  warp_argmax(bv, bi);
+  if (lane == 0) { redv[warp] = ent; }
+  __syncthreads();
+  float e = 0.f;
+  for (int k = 0; k < 8; ++k) e += redv[k];
+  __syncthreads();
+  if (lane == 0) { redv[warp] = bv; redi[warp] = bi; }
+  __syncthreads();
+  if (tid == 0) {
+    float b = redv[0];
+    int i = redi[0];
+    for (int k = 1; k < 8; ++k)
+      if (redv[k] > b || (redv[k] == b && redi[k] < i)) { b = redv[k]; i = redi[k]; }
+    *hb_out = e;
+    *best_out = (i == 0x7fffffff) ? 0 : i;
+  }
+  if (bad) atomicOr(flags, bad);
+}
+
+extern "C" int coda_b200_mixture(const int64_t* pisum_fx, const float* PB, int H, int C, float* pi_hat, float* m0,
+                                 float* h_before, int64_t* best_model, uint32_t* flags, coda_stream_t stream) {
+  CODA_CHECK_ARG(pisum_fx && PB && pi_hat && m0 && h_before && best_model && flags, "mixture: null pointer");
+  const int Hp = (H + 31) / 32 * 32;
+  size_t smem = (size_t)C * 4;
+  CODA_CHECK_ARG(smem <= 48 * 1024, "mixture: C=%d too large", C);
+  k_mixture<<<1, 256, smem, as_stream(stream)>>>(reinterpret_cast<const long long*>(pisum_fx), PB, H, Hp, C, pi_hat, m0,
+                                                 h_before, reinterpret_cast<long long*>(best_model), flags);
+  CODA_LAUNCH_OK("k_mixture");
+  return CODA_B200_OK;
+}

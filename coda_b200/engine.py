@@ -1,0 +1,314 @@
+"""Device-side state and kernel sequencing for one shard of the CODA acquisition path.
+
+PyTorch is used for device memory, streams and (through ``coda_b200.dist``) NCCL -- the
+arithmetic of the hot path is in the C-ABI library (``include/coda_b200.h``).
+
+Modes (what is kept between steps; results are the same):
+  ``incremental``   the normalised P(best | hypothetical) row of every pair is cached; a label of
+                    class t only invalidates the pairs of class t (coda.py:317 touches row t only)
+                    and the marginal refresh is the rank-1 column update of coda.py:319.
+  ``recompute``     every step recomputes all pairs from the tables (no row cache).
+  ``recompute_all`` additionally rebuilds all class tables and re-runs the full slab pass of
+                    ``update_pi_hat`` every step -- the reference's literal per-step work.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from . import _native as nat
+from .dist import LocalComm
+
+TIE_CAP = 256
+MODES = ("incremental", "recompute", "recompute_all")
+TABLE_BATCH_BYTES = 512 << 20
+
+
+def _ptr(t):
+    return t.data_ptr() if t is not None else None
+
+
+class Engine:
+    def __init__(self, preds: torch.Tensor, *, alpha: float, learning_rate: float, multiplier: float,
+                 uniform_prior: bool, hyp_w: float = 1.0, mode: str = "incremental", n_offset: int = 0,
+                 n_global: int | None = None, comm=None):
+        if mode not in MODES:
+            raise ValueError(f"mode must be one of {MODES}")
+        if not (isinstance(preds, torch.Tensor) and preds.is_cuda):
+            raise RuntimeError("coda_b200: dataset.preds must live on a CUDA (sm_100a) device; "
+                               "there is no CPU path in this package")
+        if preds.dtype != torch.float32 or preds.dim() != 3:
+            raise TypeError("coda_b200: preds must be a float32 (H, N, C) tensor (coda/datasets.py:14)")
+        if not preds.is_contiguous():
+            raise ValueError("coda_b200: preds must be contiguous (H, N, C)")
+        nat.require_device()
+        self.lib = nat.load()
+        self.preds = preds
+        self.dev = preds.device
+        self.H, self.N, self.C = (int(s) for s in preds.shape)
+        self.Hp = (self.H + 31) // 32 * 32
+        self.W = self.Hp // 32
+        self.P = 256
+        self.mode = mode
+        self.comm = comm or LocalComm()
+        self.n_offset = int(n_offset)
+        self.n_global = int(n_global if n_global is not None else self.N)
+        self.lr = float(learning_rate)
+        self.hyp_w = float(hyp_w)
+        self.prior_strength = 1 - alpha                       # coda.py:189
+        self.multiplier = float(multiplier)
+        self.uniform_prior = bool(uniform_prior)
+        if self.H > 1024:
+            raise NotImplementedError("coda_b200: H > 1024 models is not supported yet")
+        if self.C > 4096:
+            raise NotImplementedError("coda_b200: C > 4096 classes is not supported yet")
+        self.fx_shift = max(8, min(40, 62 - math.ceil(math.log2(self.n_global + 1))))
+        self.counters = {"launches": 0}
+        with torch.cuda.device(self.dev):
+            self._alloc_static()
+            self._construct()
+
+    # ------------------------------------------------------------------------------ utils
+    def _s(self):
+        return torch.cuda.current_stream(self.dev).cuda_stream
+
+    def _call(self, name, *args, n=1):
+        nat.check(getattr(self.lib, name)(*args), name)
+        self.counters["launches"] += n
+
+    def _z(self, shape, dtype):
+        return torch.zeros(shape, dtype=dtype, device=self.dev)
+
+    def _e(self, shape, dtype):
+        return torch.empty(shape, dtype=dtype, device=self.dev)
+
+    # --------------------------------------------------------------------------- buffers
+    def _alloc_static(self):
+        H, N, C, Hp, P = self.H, self.N, self.C, self.Hp, self.P
+        self.hard = self._e((N, H), torch.int16)              # uint16 bit patterns
+        self.pseudo = self._e((N,), torch.int32)
+        self.disagree = self._e((N,), torch.uint8)
+        self.labeled = self._z((N,), torch.uint8)
+        self.conf_fx = self._z((H, C, C), torch.int64)
+        self.D = self._e((H, C, C), torch.float32)
+        self.U = self._e((N, C), torch.float32)
+        self.pisum = self._z((C,), torch.int64)
+        self.grid = torch.linspace(1e-6, 1 - 1e-6, P).to(self.dev)   # coda.py:86, built on the host (trap T1)
+        self.dL = self._e((C, H, P), torch.float32)
+        self.G0T = self._z((C, P, Hp), torch.float32)
+        self.G1T = self._z((C, P, Hp), torch.float32)
+        self.PB = self._z((C, Hp), torch.float32)
+        self.pi_hat = self._z((C,), torch.float32)
+        self.m0 = self._z((Hp,), torch.float32)
+        self.hb = self._z((1,), torch.float32)
+        self.best_model = self._z((1,), torch.int64)
+        self.eig = self._e((N,), torch.float32)
+        self.nblocks = int(self.lib.coda_b200_eig_blocks(N))
+        self.partials = self._z((self.nblocks, 5), torch.int64)
+        # report block: one D2H copy per step.  [flags | best rec (5) | tie hdr (2) | tie idx | tie val]
+        self.rep = self._z((8 + TIE_CAP + TIE_CAP // 2,), torch.int64)
+        self.flags = self.rep[0:1].view(torch.int32)[0:1]
+        self.bestrec = self.rep[1:6]
+        self.tie_hdr = self.rep[6:8]
+        self.tie_idx = self.rep[8:8 + TIE_CAP]
+        self.tie_val = self.rep[8 + TIE_CAP:].view(torch.float32)[:TIE_CAP]
+        self.rep_host = torch.zeros(self.rep.shape, dtype=torch.int64).pin_memory()
+        self.sel = self._z((2,), torch.int64)
+        self.sel_host = torch.zeros((2,), dtype=torch.int64).pin_memory()
+        self.jvec = self._z((H,), torch.int32)
+        cls_per_batch = max(1, min(C, TABLE_BATCH_BYTES // max(1, self.lib.coda_b200_tables_scratch_bytes(H, 1))))
+        self.table_batch = int(cls_per_batch)
+        self.scratch = self._e((int(self.lib.coda_b200_tables_scratch_bytes(H, self.table_batch)),), torch.uint8)
+
+    # ---------------------------------------------------------------------- construction
+    def _construct(self):
+        H, N, C, s = self.H, self.N, self.C, self._s()
+        self._call("coda_b200_scan_slab", _ptr(self.preds), H, N, C, _ptr(self.hard), _ptr(self.pseudo),
+                   _ptr(self.disagree), _ptr(self.flags), s)
+        self._call("coda_b200_confusion_accum", _ptr(self.preds), _ptr(self.pseudo), H, N, C, self.fx_shift,
+                   _ptr(self.conf_fx), s)
+        self.comm.allreduce_sum_(self.conf_fx)
+        self._call("coda_b200_init_dirichlets", _ptr(self.conf_fx), H, C, self.fx_shift, self.prior_strength,
+                   self.multiplier, int(self.uniform_prior), _ptr(self.D), s)
+        self.conf_fx = None                                     # H*C*C int64, only needed once
+        self._refresh_marginals_full()
+        self._build_pairs()
+        self._tables(0, C)
+        self._mixture()
+        self.dirty = None            # None == every class dirty
+        self.scored = False
+        self.check_flags(sync=True)
+
+    def _refresh_marginals_full(self):
+        H, N, C, s = self.H, self.N, self.C, self._s()
+        self._call("coda_b200_pi_full", _ptr(self.preds), _ptr(self.D), H, N, C, _ptr(self.U), s)
+        self.pisum.zero_()
+        self._call("coda_b200_pi_reduce", _ptr(self.U), N, C, self.fx_shift, None, _ptr(self.pisum),
+                   _ptr(self.flags), s)
+        self.comm.allreduce_sum_(self.pisum)
+
+    def _build_pairs(self):
+        H, N, C, W, s = self.H, self.N, self.C, self.W, self._s()
+        ent_cnt = self._e((N,), torch.int32)
+        cls_heavy = self._z((C,), torch.int32)
+        self._call("coda_b200_pair_count", _ptr(self.hard), H, N, C, _ptr(ent_cnt), _ptr(cls_heavy), s)
+        self.ent_off = self._z((N + 1,), torch.int64)
+        torch.cumsum(ent_cnt, 0, out=self.ent_off[1:])          # init-time plumbing
+        heavy = cls_heavy.cpu().numpy().astype(np.int64)        # host sync (construction only)
+        n_ent = int(self.ent_off[-1].item())
+        per_cls = 1 + H + heavy
+        cls_base = np.zeros(C + 1, dtype=np.int64)
+        np.cumsum(per_cls, out=cls_base[1:])
+        self.npairs = int(cls_base[-1])
+        self.n_heavy = int(heavy.sum())
+        self.n_entries = n_ent
+        if self.npairs >= 2 ** 31:
+            raise NotImplementedError("coda_b200: more than 2^31 pairs in one shard")
+        self.cls_base_host = cls_base
+        self.cls_base = torch.from_numpy(cls_base).to(self.dev)
+        # tiles of <= 32 same-class pairs
+        nt = (per_cls + 31) // 32
+        tile_off = np.zeros(C + 1, dtype=np.int64)
+        np.cumsum(nt, out=tile_off[1:])
+        cls_of_tile = np.repeat(np.arange(C, dtype=np.int64), nt)
+        k_in_cls = np.arange(int(tile_off[-1]), dtype=np.int64) - tile_off[cls_of_tile]
+        start = cls_base[cls_of_tile] + 32 * k_in_cls
+        cnt = np.minimum(32, per_cls[cls_of_tile] - 32 * k_in_cls)
+        tiles = np.stack([cls_of_tile, start, cnt, np.zeros_like(cnt)], axis=1).astype(np.int32)
+        self.tile_off_host = tile_off
+        self.ntiles = int(tile_off[-1])
+        self.tiles = torch.from_numpy(tiles).to(self.dev)
+        self.ent_pair = self._e((max(1, n_ent),), torch.int32)
+        self.ent_cls = self._e((max(1, n_ent),), torch.int16)
+        self.zmask = self._e((self.npairs, W), torch.int32)
+        self.pair_cls = self._e((self.npairs,), torch.int16)
+        self.pair_item = torch.full((self.npairs,), -1, dtype=torch.int32, device=self.dev)
+        cursor = self._z((C,), torch.int32)
+        self._call("coda_b200_pair_fill", _ptr(self.hard), H, N, C, _ptr(self.ent_off), _ptr(self.cls_base),
+                   _ptr(cursor), _ptr(self.ent_pair), _ptr(self.ent_cls), _ptr(self.zmask), _ptr(self.pair_cls),
+                   _ptr(self.pair_item), s, n=2)
+        self.gain = self._z((self.npairs,), torch.float32)
+        self.ph_cache = self._e((self.npairs, self.Hp), torch.float32) if self.mode == "incremental" else None
+
+    # ------------------------------------------------------------------------ step pieces
+    def _tables(self, lo, hi):
+        H, C, s = self.H, self.C, self._s()
+        for b0 in range(lo, hi, self.table_batch):
+            b1 = min(hi, b0 + self.table_batch)
+            self._call("coda_b200_beta_tables", _ptr(self.D), _ptr(self.grid), H, C, self.P, self.hyp_w, b0, b1, None,
+                       _ptr(self.scratch), _ptr(self.dL), _ptr(self.G0T), _ptr(self.G1T), _ptr(self.PB),
+                       _ptr(self.flags), s, n=2)
+
+    def _mixture(self):
+        self._call("coda_b200_mixture", _ptr(self.pisum), _ptr(self.PB), self.H, self.C, _ptr(self.pi_hat),
+                   _ptr(self.m0), _ptr(self.hb), _ptr(self.best_model), _ptr(self.flags), self._s())
+
+    def _pair_rows(self, tile_lo, tile_hi):
+        self._call("coda_b200_pair_rows", _ptr(self.tiles), int(tile_lo), int(tile_hi), _ptr(self.zmask),
+                   _ptr(self.dL), _ptr(self.G0T), _ptr(self.G1T), _ptr(self.PB), _ptr(self.m0), _ptr(self.pi_hat),
+                   self.H, _ptr(self.ph_cache), _ptr(self.gain), None, None, _ptr(self.flags), self._s())
+
+    def post_label(self, idx_global: int | None, true_class: int | None, from_device_sel: bool = False):
+        """coda.py:316-319: posterior update + marginal refresh + the tables that depend on them.
+        ``from_device_sel``: the {idx, class} record is already in ``self.sel`` (device loop)."""
+        H, N, C, s = self.H, self.N, self.C, self._s()
+        if not from_device_sel:
+            loc = idx_global - self.n_offset
+            self.sel_host[0] = loc if 0 <= loc < N else -1
+            self.sel_host[1] = true_class
+            self.sel.copy_(self.sel_host, non_blocking=True)
+        self._call("coda_b200_label_row", _ptr(self.hard), H, N, _ptr(self.sel), _ptr(self.jvec), _ptr(self.labeled), s)
+        if self.comm.world > 1:
+            self.comm.share_jvec_(self.jvec, self.sel)
+        self._call("coda_b200_label_apply", _ptr(self.D), H, C, _ptr(self.sel), _ptr(self.jvec), self.lr, s)
+        if self.mode == "recompute_all":
+            self._refresh_marginals_full()
+            self._tables(0, C)
+            self.dirty = None
+        else:
+            self.pisum.zero_()
+            self._call("coda_b200_pi_rank1", _ptr(self.preds), H, N, C, _ptr(self.sel), _ptr(self.jvec), self.lr,
+                       self.fx_shift, _ptr(self.U), _ptr(self.pisum), _ptr(self.flags), s)
+            self.comm.allreduce_sum_(self.pisum)
+            if from_device_sel:
+                # class only known on the device: table refresh must read it there -> rebuild through
+                # the host-visible class when available, else all classes (handled by caller)
+                raise RuntimeError("device-resident class needs tables_from_sel()")
+            self._tables(true_class, true_class + 1)
+            if self.dirty is not None:
+                self.dirty.add(int(true_class))
+        self._mixture()
+        self.scored = False
+
+    def score(self):
+        """coda.py:235-281 + 306-309: EIG of every item, candidate arg-max, isclose tie scan (enqueue only)."""
+        if self.scored:
+            return
+        N, C, s = self.N, self.C, self._s()
+        if self.mode == "incremental":
+            if self.dirty is None:
+                self._pair_rows(0, self.ntiles)               # fills the row cache and every gain
+            else:
+                for c in sorted(self.dirty):
+                    self._pair_rows(self.tile_off_host[c], self.tile_off_host[c + 1])
+                self._call("coda_b200_pair_gain", _ptr(self.ph_cache), _ptr(self.pair_cls), self.npairs, self.H,
+                           _ptr(self.PB), _ptr(self.m0), _ptr(self.pi_hat), _ptr(self.gain), s)
+            self.dirty = set()
+        else:
+            self._pair_rows(0, self.ntiles)
+        self._call("coda_b200_eig_points", _ptr(self.U), N, C, _ptr(self.ent_off), _ptr(self.ent_pair),
+                   _ptr(self.ent_cls), _ptr(self.gain), _ptr(self.cls_base), _ptr(self.labeled), _ptr(self.disagree),
+                   self.n_offset, _ptr(self.eig), _ptr(self.partials), _ptr(self.flags), s)
+        self._call("coda_b200_select_merge", _ptr(self.partials), self.nblocks, _ptr(self.bestrec), s)
+        if self.comm.world > 1:
+            recs = self.comm.allgather(self.bestrec)            # (world, 5)
+            self._call("coda_b200_select_merge", _ptr(recs), self.comm.world, _ptr(self.bestrec), s)
+        self._call("coda_b200_ties", _ptr(self.eig), N, _ptr(self.labeled), _ptr(self.disagree), self.n_offset,
+                   _ptr(self.bestrec), TIE_CAP, _ptr(self.tie_hdr), _ptr(self.tie_idx), _ptr(self.tie_val), s, n=2)
+        self.scored = True
+
+    def fetch(self):
+        """One D2H copy of the report block + a stream sync.  Returns a dict of host values."""
+        self.rep_host.copy_(self.rep, non_blocking=True)
+        torch.cuda.current_stream(self.dev).synchronize()
+        r = self.rep_host.numpy()
+        flags = int(r[0:1].view(np.int32)[0])
+        use_a = int(r[3]) > 0
+        bits = int(r[1] if use_a else r[4])
+        best_val = float(np.array([bits & 0xFFFFFFFF], dtype=np.uint32).view(np.float32)[0])
+        best_idx = int(r[2] if use_a else r[5])
+        n_ties = int(r[6])
+        k = min(n_ties, TIE_CAP)
+        tie_idx = r[8:8 + k].copy()
+        tie_val = r[8 + TIE_CAP:].view(np.float32)[:k].copy()
+        return dict(flags=flags, use_a=use_a, n_cand=int(r[3]), best_val=best_val, best_idx=best_idx,
+                    n_ties=n_ties, tie_min=int(r[7]), tie_idx=tie_idx, tie_val=tie_val)
+
+    def check_flags(self, sync=False, flags=None):
+        if flags is None:
+            flags = int(self.flags.item()) if sync else 0
+        if not flags:
+            return
+        if flags & nat.FLAG_RANGE_INPUT and not flags & nat.FLAG_NONFINITE_INPUT:
+            raise ValueError("coda_b200: dataset.preds must hold post-softmax scores in [0, 1] (coda/datasets.py:6)")
+        names = [v for k, v in nat.FLAG_NAMES.items() if flags & k]
+        raise RuntimeError(f"[NUMERIC ERROR] {', '.join(names)} has bad values (NaN/Inf)")   # util.py:20-25
+
+    def mark_labeled(self, idx_global: int):
+        loc = idx_global - self.n_offset
+        if 0 <= loc < self.N:
+            self.labeled[loc] = 1
+        self.scored = False
+
+    # ------------------------------------------------------------------------- read-outs
+    def pbest(self) -> torch.Tensor:
+        return self.m0[: self.H].clone().view(1, self.H)        # coda.py:329 -> (1, H)
+
+    def pi_hat_xi(self) -> torch.Tensor:
+        xi = torch.empty_like(self.U)
+        scratch = torch.zeros_like(self.pisum)
+        self._call("coda_b200_pi_reduce", _ptr(self.U), self.N, self.C, self.fx_shift, _ptr(xi), _ptr(scratch),
+                   _ptr(self.flags), self._s())
+        return xi

@@ -33,14 +33,15 @@ SIGNATURES = {
     "coda_b200_version": (i32, []),
     "coda_b200_sm_count": (i32, []),
     "coda_b200_device_check": (i32, []),
-    "coda_b200_scan_slab": (i32, [p, i32, i64, i32, p, p, p, p, p]),
+    "coda_b200_scan_slab": (i32, [p, i32, i64, i32, p, p, p, p, p, p]),
     "coda_b200_confusion_accum": (i32, [p, p, i32, i64, i32, i32, p, p]),
     "coda_b200_init_dirichlets": (i32, [p, i32, i32, i32, f64, f64, i32, p, p]),
     "coda_b200_pi_full": (i32, [p, p, i32, i64, i32, p, p]),
     "coda_b200_pi_reduce": (i32, [p, i64, i32, i32, p, p, p, p]),
     "coda_b200_label_row": (i32, [p, i32, i64, p, p, p, p]),
     "coda_b200_label_apply": (i32, [p, i32, i32, p, p, f64, p]),
-    "coda_b200_pi_rank1": (i32, [p, i32, i64, i32, p, p, f64, i32, p, p, p, p]),
+    "coda_b200_pi_rank1": (i32, [p, p, i32, i64, i32, p, p, f64, i32, p, p, p, p, p]),
+    "coda_b200_set_l2_fetch_granularity": (i32, [i32]),
     "coda_b200_tables_scratch_bytes": (sz, [i32, i32]),
     "coda_b200_beta_tables": (i32, [p, p, i32, i32, i32, f64, i32, i32, p, p, p, p, p, p, p, p]),
     "coda_b200_mixture": (i32, [p, p, i32, i32, p, p, p, p, p, p]),

@@ -46,3 +46,9 @@ extern "C" int coda_b200_device_check(void) {
   }
   return CODA_B200_OK;
 }
+
+extern "C" int coda_b200_set_l2_fetch_granularity(int bytes) {
+  CODA_CHECK_ARG(bytes == 32 || bytes == 64 || bytes == 128, "l2 fetch granularity must be 32, 64 or 128");
+  CODA_CUDA_OK(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)bytes));
+  return CODA_B200_OK;
+}

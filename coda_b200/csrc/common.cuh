@@ -70,16 +70,19 @@ __device__ __forceinline__ void warp_argmax(float& v, int& i) {
 }
 
 // ---- entropy term, coda.py:254/276: f(m) = -max(m,1e-12) * log2(max(m,1e-12)) ----------
+// MUFU.LG2 (abs error <= 2^-22 on [0.5, 2], 2 ulp elsewhere; q is never denormal): the gain sums
+// differences of these terms and stays ~1e-8 accurate, far inside the 5e-6 EIG parity budget.
 __device__ __forceinline__ float ent_term(float m) {
   float q = fmaxf(m, 1e-12f);
-  return -q * log2f(q);
+  return -q * __log2f(q);
 }
 
 // ---- fixed-point accumulation (order- and shard-count-independent sums) ---------------
 // Values in [0, 1] are scaled by 2^shift and summed as int64; the host picks shift so that
 // N_global * 2^shift < 2^62.
-__device__ __forceinline__ long long to_fx(float v, int shift) {
-  return __double2ll_rn(ldexp((double)v, shift));
+// `scale` = 2^shift as a float: v * scale is exact in fp32 (power-of-two scaling), so one F2I suffices.
+__device__ __forceinline__ long long to_fx(float v, float scale) {
+  return __float2ll_rn(v * scale);
 }
 __host__ __device__ __forceinline__ double from_fx(long long v, int shift) {
   return ldexp((double)v, -shift);

@@ -307,7 +307,8 @@ __global__ void __launch_bounds__(256) k_pair_rows(PairRowsArgs a, int tile0) {
   __syncthreads();
 
   // ---- normalise + information gain: one warp per pair ---------------------------------
-  const float pic = a.pi_hat[c];
+  const bool want_gain = a.gain != nullptr;       // cache-only refresh: m0 / pi_hat may not be final yet
+  const float pic = want_gain ? a.pi_hat[c] : 0.f;
   const float* pbrow = a.PB + (size_t)c * Hp;
   uint32_t bad = 0;
   for (int p = warp; p < cnt; p += 8) {
@@ -323,14 +324,18 @@ __global__ void __launch_bounds__(256) k_pair_rows(PairRowsArgs a, int tile0) {
       float ph = 0.f;
       if (h < H) {
         ph = pr[h] / den;
-        const float m = a.m0[h];
-        const float mix = m + pic * (ph - pbrow[h]);            // coda.py:274-275
-        g += ent_term(m) - ent_term(mix);                       // coda.py:254, 276
+        if (want_gain) {
+          const float m = a.m0[h];
+          const float mix = m + pic * (ph - pbrow[h]);          // coda.py:274-275
+          g += ent_term(m) - ent_term(mix);                     // coda.py:254, 276
+        }
       }
       if (cache) cache[h] = ph;
     }
-    g = warp_sum(g);
-    if (lane == 0) a.gain[pid0 + p] = g;
+    if (want_gain) {
+      g = warp_sum(g);
+      if (lane == 0) a.gain[pid0 + p] = g;
+    }
   }
   if (bad) atomicOr(a.flags, bad);
 }
@@ -345,7 +350,8 @@ extern "C" int coda_b200_pair_rows(const int32_t* tiles, int tile_lo, int tile_h
                                    const float* m0, const float* pi_hat, int H, float* ph_cache, float* gain,
                                    const int64_t* sel, const int64_t* tile_off, uint32_t* flags,
                                    coda_stream_t stream) {
-  CODA_CHECK_ARG(tiles && zmask && dL && G0T && G1T && PB && m0 && pi_hat && gain && flags, "pair_rows: null pointer");
+  CODA_CHECK_ARG(tiles && zmask && dL && G0T && G1T && PB && flags, "pair_rows: null pointer");
+  CODA_CHECK_ARG((gain && m0 && pi_hat) || (!gain && ph_cache), "pair_rows: need gain (+m0, pi_hat) or ph_cache");
   CODA_CHECK_ARG(H >= 1 && H <= 1024, "pair_rows: H=%d out of range", H);
   if (tile_hi <= tile_lo) return CODA_B200_OK;
   PairRowsArgs a;
@@ -376,34 +382,130 @@ extern "C" int coda_b200_pair_rows(const int32_t* tiles, int tile_lo, int tile_h
 
 // ---------------------------------------------------------------------------------------
 // pair_gain: information gain of every pair from the cached P(best | hypothetical) rows.
-// HBM-bound stream over ph_cache; one warp per pair.
+// HBM-bound stream over ph_cache: one warp per pair, 128-bit loads, two pairs in flight per warp.
 // ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float gain4(const float4 ph, const float4 pb, const float4 m, const float4 fm, float pic) {
+  float g = fm.x - ent_term(m.x + pic * (ph.x - pb.x));
+  g += fm.y - ent_term(m.y + pic * (ph.y - pb.y));
+  g += fm.z - ent_term(m.z + pic * (ph.z - pb.z));
+  g += fm.w - ent_term(m.w + pic * (ph.w - pb.w));
+  return g;
+}
+
 __global__ void __launch_bounds__(256) k_pair_gain(const float* __restrict__ ph_cache,
                                                    const uint16_t* __restrict__ pair_cls, long long npairs, int H,
                                                    int Hp, const float* __restrict__ PB, const float* __restrict__ m0,
                                                    const float* __restrict__ pi_hat, float* __restrict__ gain) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* m0s = reinterpret_cast<float*>(smem_raw);   // [Hp]
-  float* fm0 = m0s + Hp;                             // [Hp]  f(m0)
+  float* fm0 = m0s + Hp;                             // [Hp]  f(m0); padded models carry f(0) so they cancel
   for (int h = threadIdx.x; h < Hp; h += blockDim.x) {
-    float m = m0[h];
+    float m = h < H ? m0[h] : 0.f;
     m0s[h] = m;
-    fm0[h] = h < H ? ent_term(m) : 0.f;
+    fm0[h] = ent_term(m);
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (long long pid = (long long)blockIdx.x * 8 + warp; pid < npairs; pid += (long long)gridDim.x * 8) {
-    const int c = pair_cls[pid];
-    const float pic = pi_hat[c];
-    const float* pr = ph_cache + (size_t)pid * Hp;
-    const float* pbrow = PB + (size_t)c * Hp;
-    float g = 0.f;
-    for (int h = lane; h < H; h += 32) {
-      const float mix = m0s[h] + pic * (__ldg(pr + h) - __ldg(pbrow + h));
-      g += fm0[h] - ent_term(mix);
+  const long long stride = (long long)gridDim.x * 8;
+  const int nq = Hp >> 7;           // float4 per lane per row, full 128-float groups
+  const int rem = Hp & 127;         // Hp is a multiple of 32: remainder handled with a lane mask
+  for (long long pid = (long long)blockIdx.x * 8 + warp; pid < npairs; pid += 2 * stride) {
+    const long long pid2 = pid + stride;
+    const bool has2 = pid2 < npairs;
+    const int c1 = pair_cls[pid];
+    const int c2 = has2 ? pair_cls[pid2] : c1;
+    const float pic1 = pi_hat[c1], pic2 = pi_hat[c2];
+    const float4* r1 = reinterpret_cast<const float4*>(ph_cache + (size_t)pid * Hp);
+    const float4* r2 = reinterpret_cast<const float4*>(ph_cache + (size_t)(has2 ? pid2 : pid) * Hp);
+    const float4* b1 = reinterpret_cast<const float4*>(PB + (size_t)c1 * Hp);
+    const float4* b2 = reinterpret_cast<const float4*>(PB + (size_t)c2 * Hp);
+    const float4* ms = reinterpret_cast<const float4*>(m0s);
+    const float4* fs = reinterpret_cast<const float4*>(fm0);
+    float g1 = 0.f, g2 = 0.f;
+    int q = 0;
+    for (; q < nq; ++q) {
+      const int i = q * 32 + lane;
+      const float4 a1 = __ldg(r1 + i), a2 = __ldg(r2 + i);
+      const float4 p1 = __ldg(b1 + i), p2 = __ldg(b2 + i);
+      const float4 m = ms[i], fm = fs[i];
+      g1 += gain4(a1, p1, m, fm, pic1);
+      g2 += gain4(a2, p2, m, fm, pic2);
     }
-    g = warp_sum(g);
-    if (lane == 0) gain[pid] = g;
+    if (rem && lane * 4 < rem) {
+      const int i = nq * 32 + lane;
+      const float4 a1 = __ldg(r1 + i), a2 = __ldg(r2 + i);
+      const float4 p1 = __ldg(b1 + i), p2 = __ldg(b2 + i);
+      const float4 m = ms[i], fm = fs[i];
+      g1 += gain4(a1, p1, m, fm, pic1);
+      g2 += gain4(a2, p2, m, fm, pic2);
+    }
+    g1 = warp_sum(g1);
+    g2 = warp_sum(g2);
+    if (lane == 0) {
+      gain[pid] = g1;
+      if (has2) gain[pid2] = g2;
+    }
+  }
+}
+
+// Fast path for Hp = 128 * NQ: pairs are class-sorted, so the class row PB[c], m0 and f(m0) live in
+// registers across a run of pairs and the only traffic is the cached row itself, four pairs in flight.
+template <int NQ>
+__global__ void __launch_bounds__(256) k_pair_gain_fast(const float* __restrict__ ph_cache,
+                                                        const uint16_t* __restrict__ pair_cls, long long npairs,
+                                                        int H, const float* __restrict__ PB,
+                                                        const float* __restrict__ m0,
+                                                        const float* __restrict__ pi_hat, float* __restrict__ gain) {
+  constexpr int Hp = 128 * NQ;
+  constexpr int CH = 32;   // pairs per warp chunk
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float4 m[NQ], fm[NQ], pb[NQ];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    const int h = (q * 32 + lane) * 4;
+    float4 v = __ldg(reinterpret_cast<const float4*>(m0) + q * 32 + lane);
+    if (h + 0 >= H) v.x = 0.f;
+    if (h + 1 >= H) v.y = 0.f;
+    if (h + 2 >= H) v.z = 0.f;
+    if (h + 3 >= H) v.w = 0.f;
+    m[q] = v;
+    fm[q] = make_float4(ent_term(v.x), ent_term(v.y), ent_term(v.z), ent_term(v.w));
+    pb[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  int cur = -1;
+  float pic = 0.f;
+  const long long nchunks = (npairs + CH - 1) / CH;
+  for (long long ch = (long long)blockIdx.x * 8 + warp; ch < nchunks; ch += (long long)gridDim.x * 8) {
+    const long long p0 = ch * CH;
+    const long long p1 = min(npairs, p0 + CH);
+    for (long long i = p0; i < p1; i += 4) {
+      float4 a[4][NQ];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const long long pid = min(i + j, npairs - 1);
+        const float4* r = reinterpret_cast<const float4*>(ph_cache + (size_t)pid * Hp);
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) a[j][q] = __ldg(r + q * 32 + lane);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const long long pid = i + j;
+        if (pid < p1) {
+          const int c = pair_cls[pid];
+          if (c != cur) {
+            cur = c;
+            pic = pi_hat[c];
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) pb[q] = __ldg(reinterpret_cast<const float4*>(PB + (size_t)c * Hp) + q * 32 + lane);
+          }
+          float g = 0.f;
+#pragma unroll
+          for (int q = 0; q < NQ; ++q) g += gain4(a[j][q], pb[q], m[q], fm[q], pic);
+          g = warp_sum(g);
+          if (lane == 0) gain[pid] = g;
+        }
+      }
+    }
   }
 }
 
@@ -412,10 +514,21 @@ extern "C" int coda_b200_pair_gain(const float* ph_cache, const uint16_t* pair_c
                                    coda_stream_t stream) {
   CODA_CHECK_ARG(ph_cache && pair_cls && PB && m0 && pi_hat && gain, "pair_gain: null pointer");
   const int Hp = (H + 31) / 32 * 32;
+  cudaStream_t st = as_stream(stream);
+  if (Hp % 128 == 0 && Hp <= 512) {
+    int grid = (int)min((long long)(npairs + 255) / 256, (long long)coda_sm_count() * 6);
+    if (grid < 1) grid = 1;
+    if (Hp == 128) k_pair_gain_fast<1><<<grid, 256, 0, st>>>(ph_cache, pair_cls, npairs, H, PB, m0, pi_hat, gain);
+    else if (Hp == 256) k_pair_gain_fast<2><<<grid, 256, 0, st>>>(ph_cache, pair_cls, npairs, H, PB, m0, pi_hat, gain);
+    else if (Hp == 384) k_pair_gain_fast<3><<<grid, 256, 0, st>>>(ph_cache, pair_cls, npairs, H, PB, m0, pi_hat, gain);
+    else k_pair_gain_fast<4><<<grid, 256, 0, st>>>(ph_cache, pair_cls, npairs, H, PB, m0, pi_hat, gain);
+    CODA_LAUNCH_OK("k_pair_gain_fast");
+    return CODA_B200_OK;
+  }
   size_t smem = (size_t)2 * Hp * 4;
-  int grid = (int)min((long long)(npairs + 7) / 8, (long long)coda_sm_count() * 8);
+  int grid = (int)min((long long)(npairs + 15) / 16, (long long)coda_sm_count() * 8);
   if (grid < 1) grid = 1;
-  k_pair_gain<<<grid, 256, smem, as_stream(stream)>>>(ph_cache, pair_cls, npairs, H, Hp, PB, m0, pi_hat, gain);
+  k_pair_gain<<<grid, 256, smem, st>>>(ph_cache, pair_cls, npairs, H, Hp, PB, m0, pi_hat, gain);
   CODA_LAUNCH_OK("k_pair_gain");
   return CODA_B200_OK;
 }

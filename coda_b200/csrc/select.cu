@@ -28,6 +28,8 @@ __device__ __forceinline__ void best_warp(Best& b) {
 #define IDX_NONE 0x7fffffffffffffffLL
 
 // partial record per block: 5 x int64 {bits(vA), iA, cntA, bits(vB), iB}
+// One warp per item.  KC = ceil(C / 32) register slots hold the item's U row (KC = 0: generic loop).
+template <int KC>
 __global__ void __launch_bounds__(256) k_eig_points(const float* __restrict__ U, long long N, int C,
                                                     const long long* __restrict__ ent_off,
                                                     const int32_t* __restrict__ ent_pair,
@@ -49,30 +51,84 @@ __global__ void __launch_bounds__(256) k_eig_points(const float* __restrict__ U,
   Best bA{-INFINITY, IDX_NONE}, bB{-INFINITY, IDX_NONE};
   long long cntA = 0;
   uint32_t bad = 0;
-  for (long long n = (long long)blockIdx.x * 8 + warp; n < N; n += (long long)gridDim.x * 8) {
-    const float* urow = U + (size_t)n * C;
-    float s = 0.f;
-    for (int c = lane; c < C; c += 32) s += urow[c];
-    s = warp_sum(s);
-    const float den = fmaxf(s, 1e-12f);                              // coda.py:230
-    float e = 0.f;
-    for (int c = lane; c < C; c += 32) e = fmaf(urow[c] / den, g0[c], e);
-    const long long o0 = ent_off[n], o1 = ent_off[n + 1];
-    for (long long k = o0 + lane; k < o1; k += 32) {
-      const int c = ent_cls[k];
-      e = fmaf(urow[c] / den, gain[ent_pair[k]] - g0[c], e);
+  // software pipeline over the items of this warp: the row, CSR bounds and first 32 entries of item n+stride
+  // are in flight while item n is reduced, so only the gain gather is exposed per iteration.
+  const long long stride = (long long)gridDim.x * 8;
+  long long n = (long long)blockIdx.x * 8 + warp;
+  float u[KC > 0 ? KC : 1];
+  long long o0 = 0, o1 = 0;
+  int ec = -1, ep = 0;
+  auto load_row = [&](long long nn, float (&dst)[KC > 0 ? KC : 1]) {
+    if (KC > 0) {
+      const float* r = U + (size_t)nn * C;
+#pragma unroll
+      for (int k = 0; k < (KC > 0 ? KC : 1); ++k) {
+        const int c = lane + 32 * k;
+        dst[k] = c < C ? __ldg(r + c) : 0.f;
+      }
     }
+  };
+  if (n < N) {
+    load_row(n, u);
+    o0 = __ldg(ent_off + n);
+    o1 = __ldg(ent_off + n + 1);
+    if (o0 + lane < o1) { ec = ent_cls[o0 + lane]; ep = ent_pair[o0 + lane]; }
+  }
+  while (n < N) {
+    const long long nn = n + stride;
+    const float* urow = U + (size_t)n * C;
+    float un[KC > 0 ? KC : 1];
+    long long o0n = 0, o1n = 0;
+    if (nn < N) {
+      load_row(nn, un);
+      o0n = __ldg(ent_off + nn);
+      o1n = __ldg(ent_off + nn + 1);
+    }
+    float eg = 0.f, eu = 0.f;
+    if (ec >= 0) { eg = __ldg(gain + ep); eu = __ldg(urow + ec); }
+    float s = 0.f, e = 0.f;
+    if (KC > 0) {
+#pragma unroll
+      for (int k = 0; k < (KC > 0 ? KC : 1); ++k) {
+        const int c = lane + 32 * k;
+        s += u[k];
+        if (c < C) e = fmaf(u[k], g0[c], e);
+      }
+    } else {
+      for (int c = lane; c < C; c += 32) {
+        const float v = __ldg(urow + c);
+        s += v;
+        e = fmaf(v, g0[c], e);
+      }
+    }
+    if (ec >= 0) e = fmaf(eu, eg - g0[ec], e);
+    for (long long k0 = o0 + lane + 32; k0 < o1; k0 += 32) {   // items with more than 32 distinct predicted classes
+      const int c = ent_cls[k0];
+      e = fmaf(__ldg(urow + c), __ldg(gain + ent_pair[k0]) - g0[c], e);
+    }
+    // next item's entries (their addresses depend on o0n, which has had the reductions above to arrive)
+    int ecn = -1, epn = 0;
+    if (nn < N && o0n + lane < o1n) { ecn = ent_cls[o0n + lane]; epn = ent_pair[o0n + lane]; }
+    s = warp_sum(s);
     e = warp_sum(e);
     if (lane == 0) {
-      eig[n] = e;
-      if (!isfinite(e)) bad |= CODA_B200_FLAG_NONFINITE_EIG;
+      // eig = sum_c xi_c * gain_c with xi = U / max(sum U, 1e-12) (coda.py:230, 278): one division per item
+      const float v = e / fmaxf(s, 1e-12f);
+      eig[n] = v;
+      if (!isfinite(v)) bad |= CODA_B200_FLAG_NONFINITE_EIG;
       if (!labeled[n]) {
-        best_update(bB, e, n_offset + n);
+        best_update(bB, v, n_offset + n);
         if (disagree[n]) {
-          best_update(bA, e, n_offset + n);
+          best_update(bA, v, n_offset + n);
           ++cntA;
         }
       }
+    }
+    n = nn;
+    o0 = o0n; o1 = o1n; ec = ecn; ep = epn;
+    if (KC > 0) {
+#pragma unroll
+      for (int k = 0; k < (KC > 0 ? KC : 1); ++k) u[k] = un[k];
     }
   }
   if (lane == 0) {
@@ -96,7 +152,7 @@ __global__ void __launch_bounds__(256) k_eig_points(const float* __restrict__ U,
 
 extern "C" int coda_b200_eig_blocks(int64_t N) {
   long long want = (N + 7) / 8;
-  long long cap = (long long)coda_sm_count() * 8;
+  long long cap = (long long)coda_sm_count() * 16;
   return (int)(want < cap ? (want < 1 ? 1 : want) : cap);
 }
 
@@ -109,10 +165,16 @@ extern "C" int coda_b200_eig_points(const float* U, int64_t N, int C, const int6
   size_t smem = (size_t)C * 4;
   CODA_CHECK_ARG(smem <= 48 * 1024, "eig_points: C=%d too large", C);
   int grid = coda_b200_eig_blocks(N);
-  k_eig_points<<<grid, 256, smem, as_stream(stream)>>>(U, N, C, reinterpret_cast<const long long*>(ent_off), ent_pair,
-                                                       ent_cls, gain, reinterpret_cast<const long long*>(cls_base),
-                                                       labeled, disagree, n_offset, eig,
-                                                       reinterpret_cast<long long*>(partials), flags);
+#define LAUNCH_EP(KC)                                                                                              \
+  k_eig_points<KC><<<grid, 256, smem, as_stream(stream)>>>(                                                        \
+      U, N, C, reinterpret_cast<const long long*>(ent_off), ent_pair, ent_cls, gain,                               \
+      reinterpret_cast<const long long*>(cls_base), labeled, disagree, n_offset, eig,                              \
+      reinterpret_cast<long long*>(partials), flags)
+  if (C <= 32) LAUNCH_EP(1);
+  else if (C <= 64) LAUNCH_EP(2);
+  else if (C <= 128) LAUNCH_EP(4);
+  else LAUNCH_EP(0);
+#undef LAUNCH_EP
   CODA_LAUNCH_OK("k_eig_points");
   return CODA_B200_OK;
 }

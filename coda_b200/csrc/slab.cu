@@ -17,7 +17,7 @@
 __global__ void __launch_bounds__(256) k_scan_slab(const float* __restrict__ preds, int H, long long N, int C,
                                                    int TN, uint16_t* __restrict__ hard,
                                                    int32_t* __restrict__ pseudo, uint8_t* __restrict__ disagree,
-                                                   uint32_t* __restrict__ flags) {
+                                                   float* __restrict__ ens_out, uint32_t* __restrict__ flags) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* ens = reinterpret_cast<float*>(smem_raw);                       // [TN][C]
   uint16_t* hard_t = reinterpret_cast<uint16_t*>(ens + (size_t)TN * C);  // [TN][H]
@@ -51,6 +51,10 @@ __global__ void __launch_bounds__(256) k_scan_slab(const float* __restrict__ pre
     uint16_t* dst = hard + (size_t)n0 * H;
     for (int i = threadIdx.x; i < tn * H; i += blockDim.x) dst[i] = hard_t[i];
   }
+  if (ens_out) {   // E[n][c] = sum_h preds[h][n][c], reused by pi_rank1's ensemble shortcut
+    float* dst = ens_out + (size_t)n0 * C;
+    for (int i = threadIdx.x; i < tn * C; i += blockDim.x) dst[i] = ens[i];
+  }
   const float fH = (float)H;
   for (int p = warp; p < tn; p += nwarp) {
     const float* erow = ens + (size_t)p * C;
@@ -75,7 +79,7 @@ __global__ void __launch_bounds__(256) k_scan_slab(const float* __restrict__ pre
 }
 
 extern "C" int coda_b200_scan_slab(const float* preds, int H, int64_t N, int C, uint16_t* hard, int32_t* pseudo,
-                                   uint8_t* disagree, uint32_t* flags, coda_stream_t stream) {
+                                   uint8_t* disagree, float* ens_out, uint32_t* flags, coda_stream_t stream) {
   CODA_CHECK_ARG(preds && hard && pseudo && disagree && flags, "scan_slab: null pointer");
   CODA_CHECK_ARG(H >= 1 && C >= 2 && C <= 65535 && N >= 1, "scan_slab: bad dims H=%d N=%lld C=%d", H, (long long)N, C);
   int TN = 32;
@@ -88,7 +92,7 @@ extern "C" int coda_b200_scan_slab(const float* preds, int H, int64_t N, int C, 
   CODA_CHECK_ARG(need <= 200 * 1024, "scan_slab: H=%d C=%d does not fit shared memory", H, C);
   CODA_CUDA_OK(cudaFuncSetAttribute(k_scan_slab, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
   long long grid = (N + TN - 1) / TN;
-  k_scan_slab<<<(unsigned)grid, 256, need, as_stream(stream)>>>(preds, H, N, C, TN, hard, pseudo, disagree, flags);
+  k_scan_slab<<<(unsigned)grid, 256, need, as_stream(stream)>>>(preds, H, N, C, TN, hard, pseudo, disagree, ens_out, flags);
   CODA_LAUNCH_OK("k_scan_slab");
   return CODA_B200_OK;
 }
@@ -100,7 +104,7 @@ extern "C" int coda_b200_scan_slab(const float* preds, int H, int64_t N, int C, 
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_confusion_accum(const float* __restrict__ preds,
                                                          const int32_t* __restrict__ pseudo, int H, long long N,
-                                                         int C, int shift, long long chunk, int use_smem,
+                                                         int C, float fxs, long long chunk, int use_smem,
                                                          unsigned long long* __restrict__ conf_fx) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned long long* tab = reinterpret_cast<unsigned long long*>(smem_raw);  // [C][C]
@@ -119,7 +123,7 @@ __global__ void __launch_bounds__(256) k_confusion_accum(const float* __restrict
     const float* row = preds + ((size_t)h * N + n) * C;
     unsigned long long* dst = dst_tab + (size_t)y * C;
     for (int j = lane; j < C; j += 32) {
-      long long v = to_fx(__ldg(row + j), shift);
+      long long v = to_fx(__ldg(row + j), fxs);
       if (v != 0) atomicAdd(dst + j, (unsigned long long)v);
     }
   }
@@ -143,7 +147,7 @@ extern "C" int coda_b200_confusion_accum(const float* preds, const int32_t* pseu
   long long chunk = 8192;
   long long chunks = (N + chunk - 1) / chunk;
   dim3 grid((unsigned)chunks, (unsigned)H);
-  k_confusion_accum<<<grid, 256, smem, as_stream(stream)>>>(preds, pseudo, H, N, C, fx_shift, chunk, use_smem,
+  k_confusion_accum<<<grid, 256, smem, as_stream(stream)>>>(preds, pseudo, H, N, C, exp2f((float)fx_shift), chunk, use_smem,
                                                            reinterpret_cast<unsigned long long*>(conf_fx));
   CODA_LAUNCH_OK("k_confusion_accum");
   return CODA_B200_OK;
@@ -262,7 +266,7 @@ extern "C" int coda_b200_pi_full(const float* preds, const float* D, int H, int6
 // shared tail of pi_reduce / pi_rank1: one warp normalises one row of U and accumulates the
 // per-class column sums of pi_hat_xi (fixed point) into a warp-private shared-memory vector.
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ void row_accumulate(float* __restrict__ urow, int C, int lane, int shift, int t,
+__device__ __forceinline__ void row_accumulate(float* __restrict__ urow, int C, int lane, float fxs, int t,
                                                float delta_t, float* __restrict__ xi_out,
                                                long long* __restrict__ wacc, uint32_t& bad) {
   float s = 0.f;
@@ -281,11 +285,11 @@ __device__ __forceinline__ void row_accumulate(float* __restrict__ urow, int C, 
     float xi = urow[c] / den;   // column t was rewritten above by this same lane
 
     if (xi_out) xi_out[c] = xi;
-    wacc[c] += to_fx(xi, shift);
+    wacc[c] += to_fx(xi, fxs);
   }
 }
 
-__global__ void __launch_bounds__(256) k_pi_reduce(float* __restrict__ U, long long N, int C, int shift,
+__global__ void __launch_bounds__(256) k_pi_reduce(float* __restrict__ U, long long N, int C, float fxs,
                                                    float* __restrict__ xi_out,
                                                    unsigned long long* __restrict__ pisum_fx,
                                                    uint32_t* __restrict__ flags) {
@@ -297,7 +301,7 @@ __global__ void __launch_bounds__(256) k_pi_reduce(float* __restrict__ U, long l
   __syncwarp();
   uint32_t bad = 0;
   for (long long n = (long long)blockIdx.x * nwarp + warp; n < N; n += (long long)gridDim.x * nwarp)
-    row_accumulate(U + (size_t)n * C, C, lane, shift, -1, 0.f, xi_out ? xi_out + (size_t)n * C : nullptr, wacc, bad);
+    row_accumulate(U + (size_t)n * C, C, lane, fxs, -1, 0.f, xi_out ? xi_out + (size_t)n * C : nullptr, wacc, bad);
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     long long s = 0;
@@ -315,7 +319,7 @@ extern "C" int coda_b200_pi_reduce(float* U, int64_t N, int C, int fx_shift, flo
   CODA_CUDA_OK(cudaFuncSetAttribute(k_pi_reduce, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   long long want = (N + 7) / 8;
   int grid = (int)min(want, (long long)coda_sm_count() * 8);
-  k_pi_reduce<<<grid, 256, smem, as_stream(stream)>>>(U, N, C, fx_shift, xi_out,
+  k_pi_reduce<<<grid, 256, smem, as_stream(stream)>>>(U, N, C, exp2f((float)fx_shift), xi_out,
                                                       reinterpret_cast<unsigned long long*>(pisum_fx), flags);
   CODA_LAUNCH_OK("k_pi_reduce");
   return CODA_B200_OK;
@@ -364,66 +368,126 @@ extern "C" int coda_b200_label_apply(float* D, int H, int C, const int64_t* sel,
   return CODA_B200_OK;
 }
 
+// label_terms: turn jvec into the list of (sign, element offset) gathers pi_rank1 performs.
+//   direct     : sum_h preds[h][n][j_h]                                  -> H terms
+//   ensemble   : with t' = the most common j_h and E[n][c] = sum_h preds[h][n][c],
+//                sum_h preds[h][n][j_h] = E[n][t'] + sum_{h: j_h != t'} (preds[h][n][j_h] - preds[h][n][t'])
+//                -> 2*M terms (M = models that disagree with the majority on the labeled item); both
+//                elements of a disagreeing model sit in the same 400-byte row, usually the same line.
+// hdr = {nterms, t' or -1}.  The term table is then copied into __constant__ memory so that the gather
+// loop reads it through the uniform/constant path instead of the LSU.
+#define R1_MAXT 2048
+__constant__ long long c_toff[R1_MAXT];
+__constant__ float c_tsg[R1_MAXT];
+
+__global__ void __launch_bounds__(256) k_label_terms(const int32_t* __restrict__ jvec, int H, int C, long long hstride,
+                                                     int have_ens, int32_t* __restrict__ hdr,
+                                                     long long* __restrict__ toff, float* __restrict__ tsg) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int* cnt = reinterpret_cast<int*>(smem_raw);   // [C]
+  __shared__ int s_tp, s_m;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) cnt[c] = 0;
+  __syncthreads();
+  for (int h = threadIdx.x; h < H; h += blockDim.x) atomicAdd(&cnt[jvec[h]], 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int best = -1, bc = 0;
+    for (int c = 0; c < C; ++c)
+      if (cnt[c] > best) { best = cnt[c]; bc = c; }
+    s_tp = bc;
+    s_m = H - best;
+  }
+  __syncthreads();
+  const int tp = s_tp, M = s_m;
+  const bool ens = have_ens && 2 * M < H;
+  if (threadIdx.x == 0) {
+    int k = 0;
+    for (int h = 0; h < H; ++h) {
+      const int j = jvec[h];
+      if (!ens) {
+        toff[k] = (long long)h * hstride + j; tsg[k] = 1.f; ++k;
+      } else if (j != tp) {
+        toff[k] = (long long)h * hstride + j; tsg[k] = 1.f; ++k;
+        toff[k] = (long long)h * hstride + tp; tsg[k] = -1.f; ++k;
+      }
+    }
+    hdr[0] = k;
+    hdr[1] = ens ? tp : -1;
+  }
+}
+
 #define R1_TN 256
-__global__ void __launch_bounds__(256) k_pi_rank1(const float* __restrict__ preds, int H, long long N, int C,
-                                                  const long long* __restrict__ sel,
-                                                  const int32_t* __restrict__ jvec, float lr, int shift,
+__global__ void __launch_bounds__(256) k_pi_rank1(const float* __restrict__ preds, const float* __restrict__ E,
+                                                  long long N, int C, const long long* __restrict__ sel,
+                                                  const int32_t* __restrict__ hdr, float lr, float fxs,
                                                   float* __restrict__ U, unsigned long long* __restrict__ pisum_fx,
                                                   uint32_t* __restrict__ flags) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   long long* wacc_all = reinterpret_cast<long long*>(smem_raw);                 // [8][C]
   float* delta = reinterpret_cast<float*>(wacc_all + (size_t)8 * C);            // [R1_TN]
-  int32_t* js = reinterpret_cast<int32_t*>(delta + R1_TN);                      // [H]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t = (int)sel[1];
+  const int nt = hdr[0], tp = hdr[1];
   long long* wacc = wacc_all + (size_t)warp * C;
   for (int c = lane; c < C; c += 32) wacc[c] = 0;
-  for (int h = threadIdx.x; h < H; h += blockDim.x) js[h] = jvec[h];
   __syncthreads();
   uint32_t bad = 0;
-  const size_t hstride = (size_t)N * C;
   for (long long n0 = (long long)blockIdx.x * R1_TN; n0 < N; n0 += (long long)gridDim.x * R1_TN) {
     const long long n = n0 + threadIdx.x;
     float d = 0.f;
     if (n < N) {
       const float* p = preds + (size_t)n * C;
-      int h = 0;
-      for (; h + 8 <= H; h += 8) {
+      if (tp >= 0) d = __ldg(E + (size_t)n * C + tp);
+      int k = 0;
+      for (; k + 8 <= nt; k += 8) {
         float v[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = __ldg(p + (size_t)(h + k) * hstride + js[h + k]);
+        for (int q = 0; q < 8; ++q) v[q] = __ldg(p + c_toff[k + q]);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) d += v[k];
+        for (int q = 0; q < 8; ++q) d = fmaf(c_tsg[k + q], v[q], d);
       }
-      for (; h < H; ++h) d += __ldg(p + (size_t)h * hstride + js[h]);
+      for (; k < nt; ++k) d = fmaf(c_tsg[k], __ldg(p + c_toff[k]), d);
     }
     delta[threadIdx.x] = lr * d;
     __syncthreads();
     const int rows = (int)min((long long)R1_TN, N - n0);
     for (int r = warp; r < rows; r += 8)
-      row_accumulate(U + (size_t)(n0 + r) * C, C, lane, shift, t, delta[r], nullptr, wacc, bad);
+      row_accumulate(U + (size_t)(n0 + r) * C, C, lane, fxs, t, delta[r], nullptr, wacc, bad);
     __syncthreads();
   }
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    long long s = 0;
-    for (int w = 0; w < 8; ++w) s += wacc_all[(size_t)w * C + c];
-    if (s) atomicAdd(pisum_fx + c, (unsigned long long)s);
+    long long s2 = 0;
+    for (int w = 0; w < 8; ++w) s2 += wacc_all[(size_t)w * C + c];
+    if (s2) atomicAdd(pisum_fx + c, (unsigned long long)s2);
   }
   if (bad) atomicOr(flags, bad);
 }
 
-extern "C" int coda_b200_pi_rank1(const float* preds, int H, int64_t N, int C, const int64_t* sel,
-                                  const int32_t* jvec, double lr, int fx_shift, float* U, int64_t* pisum_fx,
-                                  uint32_t* flags, coda_stream_t stream) {
-  CODA_CHECK_ARG(preds && sel && jvec && U && pisum_fx && flags, "pi_rank1: null pointer");
-  size_t smem = (size_t)8 * C * 8 + R1_TN * 4 + (size_t)H * 4;
-  CODA_CHECK_ARG(smem <= 200 * 1024, "pi_rank1: C=%d H=%d too large", C, H);
+extern "C" int coda_b200_pi_rank1(const float* preds, const float* ens, int H, int64_t N, int C, const int64_t* sel,
+                                  const int32_t* jvec, double lr, int fx_shift, int32_t* terms /*[2 + 6H]*/, float* U,
+                                  int64_t* pisum_fx, uint32_t* flags, coda_stream_t stream) {
+  CODA_CHECK_ARG(preds && sel && jvec && terms && U && pisum_fx && flags, "pi_rank1: null pointer");
+  CODA_CHECK_ARG(2 * H <= R1_MAXT, "pi_rank1: H=%d too large", H);
+  CODA_CHECK_ARG((reinterpret_cast<uintptr_t>(terms) & 7) == 0, "pi_rank1: terms must be 8-byte aligned");
+  int32_t* hdr = terms;                                            // 2 ints
+  long long* toff = reinterpret_cast<long long*>(terms + 2);       // 2H int64
+  float* tsg = reinterpret_cast<float*>(toff + 2 * H);             // 2H floats
+  CODA_CHECK_ARG((size_t)C * 4 <= 48 * 1024, "pi_rank1: C=%d too large", C);
+  cudaStream_t st = as_stream(stream);
+  k_label_terms<<<1, 256, (size_t)C * 4, st>>>(jvec, H, C, (long long)N * C, ens != nullptr, hdr, toff, tsg);
+  CODA_LAUNCH_OK("k_label_terms");
+  void *d_toff = nullptr, *d_tsg = nullptr;
+  CODA_CUDA_OK(cudaGetSymbolAddress(&d_toff, c_toff));
+  CODA_CUDA_OK(cudaGetSymbolAddress(&d_tsg, c_tsg));
+  CODA_CUDA_OK(cudaMemcpyAsync(d_toff, toff, (size_t)2 * H * 8, cudaMemcpyDeviceToDevice, st));
+  CODA_CUDA_OK(cudaMemcpyAsync(d_tsg, tsg, (size_t)2 * H * 4, cudaMemcpyDeviceToDevice, st));
+  size_t smem = (size_t)8 * C * 8 + R1_TN * 4;
+  CODA_CHECK_ARG(smem <= 200 * 1024, "pi_rank1: C=%d too large", C);
   CODA_CUDA_OK(cudaFuncSetAttribute(k_pi_rank1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   long long want = (N + R1_TN - 1) / R1_TN;
   int grid = (int)min(want, (long long)coda_sm_count() * 8);
-  k_pi_rank1<<<grid, 256, smem, as_stream(stream)>>>(preds, H, N, C, reinterpret_cast<const long long*>(sel), jvec,
-                                                     (float)lr, fx_shift, U,
-                                                     reinterpret_cast<unsigned long long*>(pisum_fx), flags);
+  k_pi_rank1<<<grid, 256, smem, st>>>(preds, ens, N, C, reinterpret_cast<const long long*>(sel), hdr, (float)lr,
+                                      exp2f((float)fx_shift), U, reinterpret_cast<unsigned long long*>(pisum_fx), flags);
   CODA_LAUNCH_OK("k_pi_rank1");
   return CODA_B200_OK;
 }

@@ -88,16 +88,16 @@ __global__ void __launch_bounds__(TP_) k_beta_nodes(const float* __restrict__ D,
   if (bad) atomicOr(flags, bad);
 }
 
-// grid = (ncls); block = 256 threads, one per node.  Writes dL, G0T, G1T, PB for the class.
+// grid = (ncls, HSPLIT); block = 256 threads, one per node.  CTA (ci, sl) writes dL, G0T, G1T and the raw
+// "before" integrals for the models h = sl, sl + HSPLIT, ... of class ci.
+#define HSPLIT 8
 __global__ void __launch_bounds__(TP_) k_beta_combine(const double* __restrict__ pdf_s, const double* __restrict__ L_s,
                                                       const float* __restrict__ grid_x, int H, int Hp, int cls_lo,
-                                                      const long long* __restrict__ sel, float* __restrict__ dL, float* __restrict__ G0T,
-                                                      float* __restrict__ G1T, float* __restrict__ PB,
-                                                      uint32_t* __restrict__ flags) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+                                                      const long long* __restrict__ sel, float* __restrict__ dL,
+                                                      float* __restrict__ G0T, float* __restrict__ G1T,
+                                                      double* __restrict__ pb_raw, uint32_t* __restrict__ flags) {
   if (sel) cls_lo = (int)sel[1];
-  double* part = reinterpret_cast<double*>(smem_raw);   // [8][Hp]  per-warp partial sums of the before-integrand
-  __shared__ double red[8];
+  __shared__ double part[8];
   const int ci = blockIdx.x, c = cls_lo + ci, x = threadIdx.x, ncls = gridDim.x;
   const int lane = x & 31, warp = x >> 5;
   const size_t plane = (size_t)ncls * H * TP_;
@@ -113,12 +113,12 @@ __global__ void __launch_bounds__(TP_) k_beta_combine(const double* __restrict__
   const float dr_ = x < TP_ - 1 ? grid_x[x + 1] - xf : 0.f;
   const double wq = 0.5 * ((double)dl_ + (double)dr_);
   double S0 = 0.0, SB = 0.0;
-  for (int h = 0; h < H; ++h) {
+  for (int h = 0; h < H; ++h) {   // every CTA of the class forms the same sums in the same order
     S0 += Lm[(size_t)h * TP_ + x];
     SB += Lb[(size_t)h * TP_ + x];
   }
   uint32_t bad = 0;
-  for (int h = 0; h < H; ++h) {
+  for (int h = blockIdx.y; h < H; h += HSPLIT) {
     const size_t o = (size_t)h * TP_ + x;
     const double lm = Lm[o], lh = Lh[o], lb = Lb[o];
     const double g0 = wq * pm[o] * exp(fmin(fmax(S0 - lm, -80.0), 80.0));
@@ -130,30 +130,41 @@ __global__ void __launch_bounds__(TP_) k_beta_combine(const double* __restrict__
     G0T[((size_t)c * TP_ + x) * Hp + h] = g0f;
     G1T[((size_t)c * TP_ + x) * Hp + h] = g1f;
     ib = warp_sum(ib);
-    if (lane == 0) part[(size_t)warp * Hp + h] = ib;
+    __syncthreads();
+    if (lane == 0) part[warp] = ib;
+    __syncthreads();
+    if (x == 0) {
+      double sum = 0.0;
+      for (int w8 = 0; w8 < 8; ++w8) sum += part[w8];   // fixed order
+      pb_raw[(size_t)ci * Hp + h] = sum;
+    }
   }
-  __syncthreads();
-  // PB row: sum the 8 warp partials in fixed order, normalise over h (coda.py:114)
-  double tot = 0.0;
-  for (int h = x; h < H; h += TP_) {
-    double s = 0.0;
-    for (int w8 = 0; w8 < 8; ++w8) s += part[(size_t)w8 * Hp + h];
-    part[h] = s;   // warp-0 slot reused: only this thread touches column h
-    tot += s;
-  }
-  tot = warp_sum(tot);
-  if (lane == 0) red[warp] = tot;
-  __syncthreads();
-  double total = 0.0;
-  for (int k = 0; k < 8; ++k) total += red[k];
-  if (!isfinite(total)) bad |= CODA_B200_FLAG_NONFINITE_TABLE;
-  total = fmax(total, (double)1e-30f);
-  for (int h = x; h < Hp; h += TP_) PB[(size_t)c * Hp + h] = h < H ? (float)(part[h] / total) : 0.f;
   if (bad) atomicOr(flags, bad);
 }
 
+// PB row: normalise the raw integrals over h (coda.py:114).  grid = (ncls), block = 256.
+__global__ void __launch_bounds__(TP_) k_pb_normalize(const double* __restrict__ pb_raw, int H, int Hp, int cls_lo,
+                                                      const long long* __restrict__ sel, float* __restrict__ PB,
+                                                      uint32_t* __restrict__ flags) {
+  if (sel) cls_lo = (int)sel[1];
+  __shared__ double red[8];
+  const int ci = blockIdx.x, c = cls_lo + ci, x = threadIdx.x;
+  const double* row = pb_raw + (size_t)ci * Hp;
+  double tot = 0.0;
+  for (int h = x; h < H; h += TP_) tot += row[h];
+  tot = warp_sum(tot);
+  if ((x & 31) == 0) red[x >> 5] = tot;
+  __syncthreads();
+  double total = 0.0;
+  for (int k = 0; k < 8; ++k) total += red[k];
+  if (!isfinite(total) && x == 0) atomicOr(flags, CODA_B200_FLAG_NONFINITE_TABLE);
+  total = fmax(total, (double)1e-30f);
+  for (int h = x; h < Hp; h += TP_) PB[(size_t)c * Hp + h] = h < H ? (float)(row[h] / total) : 0.f;
+}
+
 extern "C" size_t coda_b200_tables_scratch_bytes(int H, int ncls) {
-  return (size_t)2 * 3 * ncls * H * TP_ * sizeof(double);
+  const int Hp = (H + 31) / 32 * 32;
+  return (size_t)2 * 3 * ncls * H * TP_ * sizeof(double) + (size_t)ncls * Hp * sizeof(double);
 }
 
 extern "C" int coda_b200_beta_tables(const float* D, const float* grid_x, int H, int C, int P, double hyp_w,
@@ -168,14 +179,15 @@ extern "C" int coda_b200_beta_tables(const float* D, const float* grid_x, int H,
   const int Hp = (H + 31) / 32 * 32;
   double* pdf_s = reinterpret_cast<double*>(scratch);
   double* L_s = pdf_s + (size_t)3 * ncls * H * TP_;
+  double* pb_raw = L_s + (size_t)3 * ncls * H * TP_;
   dim3 g1((unsigned)H, (unsigned)ncls);
   k_beta_nodes<<<g1, TP_, 0, as_stream(stream)>>>(D, grid_x, H, C, cls_lo, (float)hyp_w, seld, pdf_s, L_s, flags);
   CODA_LAUNCH_OK("k_beta_nodes");
-  size_t smem = (size_t)8 * Hp * sizeof(double);
-  CODA_CHECK_ARG(smem <= 200 * 1024, "beta_tables: H=%d too large", H);
-  CODA_CUDA_OK(cudaFuncSetAttribute(k_beta_combine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_beta_combine<<<ncls, TP_, smem, as_stream(stream)>>>(pdf_s, L_s, grid_x, H, Hp, cls_lo, seld, dL, G0T, G1T, PB, flags);
+  dim3 g2((unsigned)ncls, HSPLIT);
+  k_beta_combine<<<g2, TP_, 0, as_stream(stream)>>>(pdf_s, L_s, grid_x, H, Hp, cls_lo, seld, dL, G0T, G1T, pb_raw, flags);
   CODA_LAUNCH_OK("k_beta_combine");
+  k_pb_normalize<<<ncls, TP_, 0, as_stream(stream)>>>(pb_raw, H, Hp, cls_lo, seld, PB, flags);
+  CODA_LAUNCH_OK("k_pb_normalize");
   return CODA_B200_OK;
 }
 

@@ -13,7 +13,9 @@ Modes (what is kept between steps; results are the same):
 """
 from __future__ import annotations
 
+import contextlib
 import math
+import os
 
 import numpy as np
 import torch
@@ -45,6 +47,8 @@ class Engine:
             raise ValueError("coda_b200: preds must be contiguous (H, N, C)")
         nat.require_device()
         self.lib = nat.load()
+        if os.environ.get("CODA_B200_L2_FETCH"):
+            nat.check(self.lib.coda_b200_set_l2_fetch_granularity(int(os.environ["CODA_B200_L2_FETCH"])), "l2_fetch")
         self.preds = preds
         self.dev = preds.device
         self.H, self.N, self.C = (int(s) for s in preds.shape)
@@ -66,6 +70,7 @@ class Engine:
             raise NotImplementedError("coda_b200: C > 4096 classes is not supported yet")
         self.fx_shift = max(8, min(40, 62 - math.ceil(math.log2(self.n_global + 1))))
         self.counters = {"launches": 0}
+        self.profile, self.profile_only = None, None
         with torch.cuda.device(self.dev):
             self._alloc_static()
             self._construct()
@@ -75,8 +80,29 @@ class Engine:
         return torch.cuda.current_stream(self.dev).cuda_stream
 
     def _call(self, name, *args, n=1):
-        nat.check(getattr(self.lib, name)(*args), name)
+        prof = self.profile
+        if prof is not None and (self.profile_only is None or name in self.profile_only):
+            st = torch.cuda.current_stream(self.dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(st)
+            rc = getattr(self.lib, name)(*args)
+            e1.record(st)
+            prof.setdefault(name, []).append((e0, e1))
+        else:
+            rc = getattr(self.lib, name)(*args)
+        nat.check(rc, name)
         self.counters["launches"] += n
+
+    def start_profile(self, only=None):
+        """Bracket every C-ABI launch (or just ``only``) with CUDA events on the launching stream."""
+        self.profile, self.profile_only = {}, (set(only) if only else None)
+
+    def stop_profile(self):
+        """-> {entry point: (launches, total ms)}; synchronises."""
+        torch.cuda.synchronize(self.dev)
+        out = {k: (len(v), float(sum(a.elapsed_time(b) for a, b in v))) for k, v in (self.profile or {}).items()}
+        self.profile = None
+        return out
 
     def _z(self, shape, dtype):
         return torch.zeros(shape, dtype=dtype, device=self.dev)
@@ -118,6 +144,9 @@ class Engine:
         self.sel = self._z((2,), torch.int64)
         self.sel_host = torch.zeros((2,), dtype=torch.int64).pin_memory()
         self.jvec = self._z((H,), torch.int32)
+        self.terms = self._z((2 + 6 * H + 2,), torch.int64).view(torch.int32)[: 2 + 6 * H]   # 8-byte aligned
+        # ensemble sums E[n][c] (N*C floats) feed pi_rank1's majority shortcut; CODA_B200_ENS=0 disables it
+        self.ens = self._e((N, C), torch.float32) if os.environ.get("CODA_B200_ENS", "1") != "0" else None
         cls_per_batch = max(1, min(C, TABLE_BATCH_BYTES // max(1, self.lib.coda_b200_tables_scratch_bytes(H, 1))))
         self.table_batch = int(cls_per_batch)
         self.scratch = self._e((int(self.lib.coda_b200_tables_scratch_bytes(H, self.table_batch)),), torch.uint8)
@@ -126,7 +155,7 @@ class Engine:
     def _construct(self):
         H, N, C, s = self.H, self.N, self.C, self._s()
         self._call("coda_b200_scan_slab", _ptr(self.preds), H, N, C, _ptr(self.hard), _ptr(self.pseudo),
-                   _ptr(self.disagree), _ptr(self.flags), s)
+                   _ptr(self.disagree), _ptr(self.ens), _ptr(self.flags), s)
         self._call("coda_b200_confusion_accum", _ptr(self.preds), _ptr(self.pseudo), H, N, C, self.fx_shift,
                    _ptr(self.conf_fx), s)
         self.comm.allreduce_sum_(self.conf_fx)
@@ -137,7 +166,9 @@ class Engine:
         self._build_pairs()
         self._tables(0, C)
         self._mixture()
-        self.dirty = None            # None == every class dirty
+        self.cache_valid = False     # incremental mode: P(best | hypothetical) rows of every pair are cached
+        self.side = torch.cuda.Stream(device=self.dev)
+        self.ev_fork, self.ev_join = torch.cuda.Event(), torch.cuda.Event()
         self.scored = False
         self.check_flags(sync=True)
 
@@ -178,6 +209,8 @@ class Engine:
         cnt = np.minimum(32, per_cls[cls_of_tile] - 32 * k_in_cls)
         tiles = np.stack([cls_of_tile, start, cnt, np.zeros_like(cnt)], axis=1).astype(np.int32)
         self.tile_off_host = tile_off
+        self.tile_off = torch.from_numpy(tile_off).to(self.dev)
+        self.max_cls_tiles = int(nt.max())
         self.ntiles = int(tile_off[-1])
         self.tiles = torch.from_numpy(tiles).to(self.dev)
         self.ent_pair = self._e((max(1, n_ent),), torch.int32)
@@ -199,22 +232,29 @@ class Engine:
             b1 = min(hi, b0 + self.table_batch)
             self._call("coda_b200_beta_tables", _ptr(self.D), _ptr(self.grid), H, C, self.P, self.hyp_w, b0, b1, None,
                        _ptr(self.scratch), _ptr(self.dL), _ptr(self.G0T), _ptr(self.G1T), _ptr(self.PB),
-                       _ptr(self.flags), s, n=2)
+                       _ptr(self.flags), s, n=3)
 
     def _mixture(self):
         self._call("coda_b200_mixture", _ptr(self.pisum), _ptr(self.PB), self.H, self.C, _ptr(self.pi_hat),
                    _ptr(self.m0), _ptr(self.hb), _ptr(self.best_model), _ptr(self.flags), self._s())
 
-    def _pair_rows(self, tile_lo, tile_hi):
+    def _pair_rows(self, tile_lo, tile_hi, gains=True, sel=False):
+        cache = _ptr(self.ph_cache)
         self._call("coda_b200_pair_rows", _ptr(self.tiles), int(tile_lo), int(tile_hi), _ptr(self.zmask),
-                   _ptr(self.dL), _ptr(self.G0T), _ptr(self.G1T), _ptr(self.PB), _ptr(self.m0), _ptr(self.pi_hat),
-                   self.H, _ptr(self.ph_cache), _ptr(self.gain), None, None, _ptr(self.flags), self._s())
+                   _ptr(self.dL), _ptr(self.G0T), _ptr(self.G1T), _ptr(self.PB),
+                   _ptr(self.m0) if gains else None, _ptr(self.pi_hat) if gains else None, self.H, cache,
+                   _ptr(self.gain) if gains else None, _ptr(self.sel) if sel else None,
+                   _ptr(self.tile_off) if sel else None, _ptr(self.flags), self._s())
 
-    def post_label(self, idx_global: int | None, true_class: int | None, from_device_sel: bool = False):
+    def post_label(self, idx_global: int | None = None, true_class: int | None = None, device_sel: bool = False):
         """coda.py:316-319: posterior update + marginal refresh + the tables that depend on them.
-        ``from_device_sel``: the {idx, class} record is already in ``self.sel`` (device loop)."""
+        ``device_sel``: the {local idx, class} record is already in ``self.sel`` on the device (host-free loop).
+
+        incremental mode: the class-t tables and the cached rows of the class-t pairs only need the new D, so
+        they are rebuilt on a side stream (FP32-pipe bound) while the main stream does the HBM-bound marginal
+        refresh; the two join before the mixture."""
         H, N, C, s = self.H, self.N, self.C, self._s()
-        if not from_device_sel:
+        if not device_sel:
             loc = idx_global - self.n_offset
             self.sel_host[0] = loc if 0 <= loc < N else -1
             self.sel_host[1] = true_class
@@ -226,19 +266,35 @@ class Engine:
         if self.mode == "recompute_all":
             self._refresh_marginals_full()
             self._tables(0, C)
-            self.dirty = None
         else:
+            main = torch.cuda.current_stream(self.dev)
+            overlap = self.mode == "incremental" and self.cache_valid
+            if overlap:
+                self.ev_fork.record(main)
+                self.side.wait_event(self.ev_fork)
+                ctx = torch.cuda.stream(self.side)
+            else:
+                ctx = contextlib.nullcontext()
+            with ctx:
+                if device_sel:
+                    self._call("coda_b200_beta_tables", _ptr(self.D), _ptr(self.grid), H, C, self.P, self.hyp_w, 0, 1,
+                               _ptr(self.sel), _ptr(self.scratch), _ptr(self.dL), _ptr(self.G0T), _ptr(self.G1T),
+                               _ptr(self.PB), _ptr(self.flags), self._s(), n=3)
+                else:
+                    self._tables(true_class, true_class + 1)
+                if overlap:     # refresh the cached rows of the class-t pairs (no gains: m0 / pi_hat not final yet)
+                    if device_sel:
+                        self._pair_rows(0, self.max_cls_tiles, gains=False, sel=True)
+                    else:
+                        self._pair_rows(self.tile_off_host[true_class], self.tile_off_host[true_class + 1], gains=False)
             self.pisum.zero_()
-            self._call("coda_b200_pi_rank1", _ptr(self.preds), H, N, C, _ptr(self.sel), _ptr(self.jvec), self.lr,
-                       self.fx_shift, _ptr(self.U), _ptr(self.pisum), _ptr(self.flags), s)
+            self._call("coda_b200_pi_rank1", _ptr(self.preds), _ptr(self.ens), H, N, C, _ptr(self.sel),
+                       _ptr(self.jvec), self.lr, self.fx_shift, _ptr(self.terms), _ptr(self.U), _ptr(self.pisum),
+                       _ptr(self.flags), s, n=4)
             self.comm.allreduce_sum_(self.pisum)
-            if from_device_sel:
-                # class only known on the device: table refresh must read it there -> rebuild through
-                # the host-visible class when available, else all classes (handled by caller)
-                raise RuntimeError("device-resident class needs tables_from_sel()")
-            self._tables(true_class, true_class + 1)
-            if self.dirty is not None:
-                self.dirty.add(int(true_class))
+            if overlap:
+                self.ev_join.record(self.side)
+                main.wait_event(self.ev_join)
         self._mixture()
         self.scored = False
 
@@ -248,14 +304,11 @@ class Engine:
             return
         N, C, s = self.N, self.C, self._s()
         if self.mode == "incremental":
-            if self.dirty is None:
-                self._pair_rows(0, self.ntiles)               # fills the row cache and every gain
-            else:
-                for c in sorted(self.dirty):
-                    self._pair_rows(self.tile_off_host[c], self.tile_off_host[c + 1])
-                self._call("coda_b200_pair_gain", _ptr(self.ph_cache), _ptr(self.pair_cls), self.npairs, self.H,
-                           _ptr(self.PB), _ptr(self.m0), _ptr(self.pi_hat), _ptr(self.gain), s)
-            self.dirty = set()
+            if not self.cache_valid:
+                self._pair_rows(0, self.ntiles, gains=False)    # fill the row cache once
+                self.cache_valid = True
+            self._call("coda_b200_pair_gain", _ptr(self.ph_cache), _ptr(self.pair_cls), self.npairs, self.H,
+                       _ptr(self.PB), _ptr(self.m0), _ptr(self.pi_hat), _ptr(self.gain), s)
         else:
             self._pair_rows(0, self.ntiles)
         self._call("coda_b200_eig_points", _ptr(self.U), N, C, _ptr(self.ent_off), _ptr(self.ent_pair),
@@ -267,10 +320,24 @@ class Engine:
             self._call("coda_b200_select_merge", _ptr(recs), self.comm.world, _ptr(self.bestrec), s)
         self._call("coda_b200_ties", _ptr(self.eig), N, _ptr(self.labeled), _ptr(self.disagree), self.n_offset,
                    _ptr(self.bestrec), TIE_CAP, _ptr(self.tie_hdr), _ptr(self.tie_idx), _ptr(self.tie_val), s, n=2)
+        if self.comm.world > 1:
+            self.rep_all = self.comm.allgather(self.rep)        # every rank's tie list, judged against the global best
         self.scored = True
+
+    def device_step(self, labels_dev: torch.Tensor, step: int, hist_idx=None, hist_q=None):
+        """One acquisition step with no host round trip (bench ``value`` loop): score, pick the lowest tied
+        index, look the label up on the device (coda/oracle.py:23-24), update the posterior."""
+        self.score()
+        if self.comm.world > 1:
+            self.comm.allreduce_min_(self.tie_hdr[1:2])
+        self._call("coda_b200_device_pick", _ptr(self.tie_hdr), _ptr(labels_dev), self.n_offset, self.N,
+                   _ptr(self.eig), _ptr(self.sel), _ptr(hist_idx), _ptr(hist_q), int(step), self._s())
+        self.post_label(device_sel=True)
 
     def fetch(self):
         """One D2H copy of the report block + a stream sync.  Returns a dict of host values."""
+        if self.comm.world > 1:
+            return self._fetch_sharded()
         self.rep_host.copy_(self.rep, non_blocking=True)
         torch.cuda.current_stream(self.dev).synchronize()
         r = self.rep_host.numpy()
@@ -285,6 +352,26 @@ class Engine:
         tie_val = r[8 + TIE_CAP:].view(np.float32)[:k].copy()
         return dict(flags=flags, use_a=use_a, n_cand=int(r[3]), best_val=best_val, best_idx=best_idx,
                     n_ties=n_ties, tie_min=int(r[7]), tie_idx=tie_idx, tie_val=tie_val)
+
+    def _fetch_sharded(self):
+        allr = self.rep_all.cpu().numpy()                       # (world, len(rep)); D2H + sync
+        r0 = allr[0]
+        flags = 0
+        for r in allr:
+            flags |= int(r[0:1].view(np.int32)[0])
+        use_a = int(r0[3]) > 0                                  # bestrec is the merged (global) record on every rank
+        bits = int(r0[1] if use_a else r0[4])
+        best_val = float(np.array([bits & 0xFFFFFFFF], dtype=np.uint32).view(np.float32)[0])
+        n_ties = int(sum(int(r[6]) for r in allr))
+        idxs, vals = [], []
+        for r in allr:
+            k = min(int(r[6]), TIE_CAP)
+            idxs.append(r[8:8 + k])
+            vals.append(r[8 + TIE_CAP:].view(np.float32)[:k])
+        return dict(flags=flags, use_a=use_a, n_cand=int(r0[3]), best_val=best_val,
+                    best_idx=int(r0[2] if use_a else r0[5]), n_ties=n_ties,
+                    tie_min=int(min(int(r[7]) for r in allr)), tie_idx=np.concatenate(idxs),
+                    tie_val=np.concatenate(vals))
 
     def check_flags(self, sync=False, flags=None):
         if flags is None:

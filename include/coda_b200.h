@@ -53,8 +53,9 @@ int coda_b200_device_check(void); /* fails loudly when no sm_100 device is prese
 
 /* One pass over the slab: per-model argmax (coda.py:217, 263, 316), ensemble-mean pseudo
  * label (coda/util.py:13-14 + coda.py:193-194), unanimity bit (coda.py:215-219). */
+/* ens_out (optional) [N][C]: E[n][c] = sum_h preds[h][n][c], the un-normalised ensemble of coda/util.py:13-14. */
 int coda_b200_scan_slab(const float* preds, int H, int64_t N, int C, uint16_t* hard, int32_t* pseudo,
-                        uint8_t* disagree, uint32_t* flags, coda_stream_t stream);
+                        uint8_t* disagree, float* ens_out, uint32_t* flags, coda_stream_t stream);
 
 /* Soft confusion sums, coda.py:42 einsum('nc,hnj->hcj').  conf_fx [H][C][C] int64 fixed point
  * (value * 2^fx_shift), ACCUMULATED into; exact and order-independent so shards can be summed. */
@@ -85,9 +86,14 @@ int coda_b200_label_row(const uint16_t* hard, int H, int64_t N, const int64_t* s
 int coda_b200_label_apply(float* D, int H, int C, const int64_t* sel, const int32_t* jvec, double lr,
                           coda_stream_t stream);
 /* update_pi_hat after the rank-1 change of D (coda.py:319): U[n][t] += lr * sum_h preds[h][n][jvec[h]],
- * then the same normalise + column sums as pi_reduce. */
-int coda_b200_pi_rank1(const float* preds, int H, int64_t N, int C, const int64_t* sel, const int32_t* jvec, double lr,
-                       int fx_shift, float* U, int64_t* pisum_fx, uint32_t* flags, coda_stream_t stream);
+ * then the same normalise + column sums as pi_reduce.  With ens != NULL (scan_slab's ens_out) the sum over
+ * models is taken as E[n][t'] + corrections for the models that disagree with the majority class t' of
+ * jvec (exact algebra, fewer gathers).  terms: int32 scratch [2 + 6*H]. */
+int coda_b200_pi_rank1(const float* preds, const float* ens, int H, int64_t N, int C, const int64_t* sel,
+                       const int32_t* jvec, double lr, int fx_shift, int32_t* terms, float* U, int64_t* pisum_fx,
+                       uint32_t* flags, coda_stream_t stream);
+/* cudaLimitMaxL2FetchGranularity hint (32/64/128 B) for the sector-gather kernels. */
+int coda_b200_set_l2_fetch_granularity(int bytes);
 
 /* ---- Beta quadrature tables (dirichlet_to_beta coda.py:14-25, compute_pbest_beta_batched
  *      coda.py:77-119, batch_update_beta coda.py:150-168) for classes [cls_lo, cls_hi) ------- */

@@ -1,0 +1,317 @@
+"""Parity of the CUDA path (through the C ABI / coda_b200.CODA) with the reference goldens and the CPU oracle.
+Run on the B200 box:  python -m pytest tests -m gpu -x -q
+
+Tolerances (the reference is fp32 with a measured EIG noise floor of ~1.2e-6):
+  EIG vector            abs 5e-6          P(best) / pi_hat      abs 1e-5 (north_star: 1e-4)
+  pi_hat_xi             rel 5e-6          dirichlet update      one fp32 add: rel 2e-7 of the golden row
+  selected index        identical wherever the reference's top-1/top-2 gap exceeds 1e-5, else epsilon-optimal
+"""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import coda_oracle, golden_names, golden_slab, load_golden
+
+pytestmark = pytest.mark.gpu
+
+EIG_ATOL = 5e-6
+
+
+def _mk(preds, labels=None, **kw):
+    from coda_b200 import CODA, TensorDataset
+    dev = torch.device("cuda:0")
+    return CODA(TensorDataset(preds.to(dev), None if labels is None else labels.to(dev)), **kw)
+
+
+def _check_pick(ref_eig, idx, golden_idx):
+    """epsilon-optimality protocol."""
+    top = np.sort(ref_eig[~np.isnan(ref_eig)])[::-1]
+    gap = top[0] - top[1] if len(top) > 1 else np.inf
+    assert ref_eig[idx] >= top[0] - EIG_ATOL
+    if gap > 1e-5:
+        assert idx == golden_idx
+
+
+@pytest.mark.parametrize("mode", ["incremental", "recompute", "recompute_all"])
+@pytest.mark.parametrize("name", [n for n in golden_names() if "cfg2" not in n])
+def test_golden_trajectory(name, mode):
+    g = load_golden(name)
+    preds, labels = golden_slab(g)
+    random.seed(0)
+    sel = _mk(preds, labels, mode=mode, **g["ctor"])
+    eng = sel.engine
+    # construction: hard predictions / unanimity are integer work -> exact
+    ref_hard = preds.argmax(-1).T.numpy()
+    assert np.array_equal(eng.hard.cpu().numpy().astype(np.int64) & 0xFFFF, ref_hard)
+    assert np.array_equal(eng.disagree.cpu().numpy().astype(bool),
+                          coda_oracle.disagreement_mask(preds.argmax(-1)).numpy())
+    np.testing.assert_allclose(sel.dirichlets.cpu().numpy(), g["init_dirichlets"], rtol=2e-6, atol=1e-7)
+    np.testing.assert_allclose(sel.pi_hat.cpu().numpy(), g["init_pi_hat"], rtol=2e-6)
+    np.testing.assert_allclose(sel.pi_hat_xi.cpu().numpy(), g["init_pi_hat_xi"], rtol=5e-6, atol=1e-9)
+    b = sel.get_best_model_prediction()
+    assert b.dim() == 0 and b.dtype == torch.int64 and int(b) == int(g["init_best_model"])     # trap T10
+    pb = sel.get_pbest()
+    assert tuple(pb.shape) == (1, int(g["H"]))
+    np.testing.assert_allclose(pb.cpu().numpy(), g["init_pbest"], atol=1e-5)
+    for k in range(int(g["steps"])):
+        idx, q = sel.get_next_item_to_label()
+        assert isinstance(idx, int) and isinstance(q, float)
+        ref = g["eig"][k]
+        cand = ~np.isnan(ref)
+        assert sel.last_report["n_cand"] == int(g["n_cand"][k]) or not sel.last_report["use_a"]
+        np.testing.assert_allclose(eng.eig.cpu().numpy()[cand], ref[cand], atol=EIG_ATOL)
+        _check_pick(ref, idx, int(g["idx"][k]))
+        assert abs(q - float(g["q"][k])) < EIG_ATOL or idx != int(g["idx"][k])
+        gi = int(g["idx"][k])                     # teacher forcing: follow the reference's pick
+        t = int(labels[gi])
+        sel.add_label(gi, t, q)
+        assert int(sel.get_best_model_prediction()) == int(g["best_model"][k])
+        np.testing.assert_allclose(sel.get_pbest().cpu().numpy()[0], g["pbest"][k], atol=1e-5)
+        np.testing.assert_allclose(sel.pi_hat.cpu().numpy(), g["pi_hat"][k], rtol=2e-6)
+        np.testing.assert_allclose(sel.dirichlets[:, t].cpu().numpy(), g["dir_row"][k], rtol=3e-7, atol=0)
+        np.testing.assert_allclose(sel.pi_hat_xi[:64].cpu().numpy(), g["xi_head"][k], rtol=5e-6, atol=1e-9)
+    np.testing.assert_allclose(sel.dirichlets.cpu().numpy(), g["final_dirichlets"], rtol=2e-6, atol=1e-7)
+    assert sel.step == int(g["steps"]) + 1
+    assert sel.labeled_idxs == [int(i) for i in g["idx"]]
+    assert len(sel.unlabeled_idxs) == int(g["N"]) - int(g["steps"])
+
+
+def test_free_running_matches_reference_indices():
+    """No teacher forcing: on this golden the reference's top-1 gaps are > 1e-5, so the picks must be identical."""
+    g = load_golden("traj_small_h32_n3000_c10")
+    preds, labels = golden_slab(g)
+    random.seed(0)
+    sel = _mk(preds, labels)
+    picks = []
+    for k in range(int(g["steps"])):
+        idx, q = sel.get_next_item_to_label()
+        picks.append(idx)
+        sel.add_label(idx, int(labels[idx]), q)
+        sel.get_best_model_prediction()
+    assert picks == [int(i) for i in g["idx"]]
+    np.testing.assert_allclose(sel.get_pbest().cpu().numpy()[0], g["pbest"][-1], atol=1e-5)
+    assert sel.stochastic == bool(g["stochastic"])
+
+
+def test_cfg2_golden_if_present():
+    """BASELINE.json configs[1]: synthetic M=64 N=50k C=10 against the reference's own CPU trajectory."""
+    names = [n for n in golden_names() if "cfg2" in n]
+    if not names:
+        pytest.skip("cfg2 golden not generated")
+    g = load_golden(names[0])
+    preds, labels = golden_slab(g)
+    random.seed(0)
+    sel = _mk(preds, labels)
+    for k in range(int(g["steps"])):
+        idx, q = sel.get_next_item_to_label()
+        ref = g["eig"][k]
+        cand = ~np.isnan(ref)
+        np.testing.assert_allclose(sel.engine.eig.cpu().numpy()[cand], ref[cand], atol=EIG_ATOL)
+        _check_pick(ref, idx, int(g["idx"][k]))
+        gi = int(g["idx"][k])
+        sel.add_label(gi, int(labels[gi]), q)
+        assert int(sel.get_best_model_prediction()) == int(g["best_model"][k])
+        np.testing.assert_allclose(sel.get_pbest().cpu().numpy()[0], g["pbest"][k], atol=1e-5)
+        np.testing.assert_array_equal(sel.dirichlets[:, int(labels[gi])].cpu().numpy() > 0, True)
+        np.testing.assert_allclose(sel.dirichlets[:, int(labels[gi])].cpu().numpy(), g["dir_row"][k], rtol=3e-7)
+
+
+def test_oracle_on_fresh_seed_and_odd_shapes():
+    """Not a golden: a shape no fixture covers (H not a multiple of 32, C not a multiple of 4), oracle run live."""
+    from coda_b200.synth import synth
+    preds, labels = synth(37, 700, 9, seed=11)
+    random.seed(0)
+    ora = coda_oracle.OracleSelector(preds)
+    random.seed(0)
+    sel = _mk(preds, labels)
+    for _ in range(3):
+        i_ref, q_ref = ora.get_next_item_to_label()
+        i, q = sel.get_next_item_to_label()
+        got = sel.engine.eig.cpu().numpy()[np.asarray(ora.last_cand)]
+        np.testing.assert_allclose(got, ora.last_q.numpy(), atol=EIG_ATOL)
+        assert i == i_ref
+        ora.add_label(i, int(labels[i]), q_ref)
+        sel.add_label(i, int(labels[i]), q)
+        assert int(ora.get_best_model_prediction()) == int(sel.get_best_model_prediction())
+        np.testing.assert_allclose(sel.get_pbest().cpu().numpy(), ora.get_pbest().numpy(), atol=1e-5)
+
+
+def test_edge_unanimous_fallback_and_h2():
+    """Every model unanimous everywhere: the prefilter is empty and the candidate set falls back to all
+    unlabeled items (coda.py:239); H=2 exercises the smallest leave-one-out product."""
+    C, H, N = 4, 2, 40
+    g = torch.Generator().manual_seed(3)
+    y = torch.randint(0, C, (N,), generator=g)
+    u = torch.rand((N, C), generator=g) * 0.05
+    base = (u / u.sum(-1, keepdim=True) * 0.3)[None].repeat(H, 1, 1)
+    base[:, torch.arange(N), y] += 0.7                       # both models predict y, item-specific scores
+    random.seed(7)
+    ora = coda_oracle.OracleSelector(base.clone())
+    i_ref, q_ref = ora.get_next_item_to_label()
+    sel = _mk(base, y)
+    assert not bool(sel.engine.disagree.any())
+    i, q = sel.get_next_item_to_label()
+    assert not sel.last_report["use_a"] and sel.last_report["n_cand"] == 0
+    np.testing.assert_allclose(sel.engine.eig.cpu().numpy(), ora.last_q.numpy(), atol=EIG_ATOL)
+    assert ora.last_q.numpy()[i] >= ora.last_q.numpy().max() - EIG_ATOL and abs(q - q_ref) < EIG_ATOL
+
+
+def test_exact_ties_consume_python_rng_like_the_reference():
+    """coda.py:306-311: two items with identical predictions tie exactly; the pick is random.choice over the
+    tied candidates in ascending order and `stochastic` flips.  Same RNG state => same pick as the oracle."""
+    from coda_b200.synth import synth
+    preds, labels = synth(10, 400, 6, seed=8)
+    random.seed(1)
+    first, _ = coda_oracle.OracleSelector(preds).get_next_item_to_label()
+    twin = (first + 137) % 400
+    preds[:, twin] = preds[:, first]
+    for seed in (1, 2, 3, 4):
+        random.seed(seed)
+        ora = coda_oracle.OracleSelector(preds)
+        i_ref, q_ref = ora.get_next_item_to_label()
+        after_ref = random.getstate()
+        assert ora.stochastic and i_ref in (first, twin)
+        random.seed(seed)
+        sel = _mk(preds, labels)
+        i, q = sel.get_next_item_to_label()
+        assert sel.last_report["n_ties"] == 2 and sel.stochastic
+        assert i == i_ref and abs(q - q_ref) < EIG_ATOL and random.getstate() == after_ref
+
+
+def test_modes_agree_and_incremental_is_exact():
+    """Size-independent property: the cached-row path must reproduce a from-scratch recompute after many labels."""
+    from coda_b200.synth import synth
+    preds, labels = synth(48, 20000, 20, seed=5)
+    sels = {}
+    for mode in ("incremental", "recompute", "recompute_all"):
+        random.seed(0)
+        sels[mode] = _mk(preds, labels, mode=mode)
+    for k in range(12):
+        picks = {}
+        for mode, s in sels.items():
+            picks[mode] = s.get_next_item_to_label()
+        e_inc = sels["incremental"].engine.eig.cpu().numpy()
+        e_rec = sels["recompute"].engine.eig.cpu().numpy()
+        e_all = sels["recompute_all"].engine.eig.cpu().numpy()
+        np.testing.assert_allclose(e_inc, e_rec, atol=2e-8, rtol=0)     # same tables, same rows: summation order only
+        np.testing.assert_allclose(e_inc, e_all, atol=1e-6, rtol=0)     # rank-1 vs full refresh of the marginals
+        idx, q = picks["incremental"]
+        for s in sels.values():
+            s.add_label(idx, int(labels[idx]), q)
+            s.get_best_model_prediction()
+        np.testing.assert_allclose(sels["incremental"].get_pbest().cpu().numpy(),
+                                   sels["recompute_all"].get_pbest().cpu().numpy(), atol=1e-6)
+    # rank-1 marginal refresh (coda.py:319 restated) vs the full slab pass after 12 labels
+    np.testing.assert_allclose(sels["incremental"].pi_hat_xi.cpu().numpy(),
+                               sels["recompute_all"].pi_hat_xi.cpu().numpy(), rtol=2e-6, atol=1e-9)
+    xi = sels["incremental"].pi_hat_xi
+    np.testing.assert_allclose(xi.sum(-1).cpu().numpy(), 1.0, atol=1e-5)
+    assert abs(float(sels["incremental"].pi_hat.sum()) - 1.0) < 1e-5
+
+
+def test_pair_structure_invariants():
+    from coda_b200.synth import synth
+    preds, labels = synth(40, 3000, 12, seed=2, dense=True)
+    sel = _mk(preds, labels)
+    e = sel.engine
+    hard = preds.argmax(-1).T.numpy()                                     # (N, H)
+    ent_off = e.ent_off.cpu().numpy()
+    ent_pair = e.ent_pair.cpu().numpy()
+    ent_cls = e.ent_cls.cpu().numpy().astype(np.int64) & 0xFFFF
+    zmask = e.zmask.cpu().numpy().astype(np.int64) & 0xFFFFFFFF
+    pair_cls = e.pair_cls.cpu().numpy().astype(np.int64) & 0xFFFF
+    base = e.cls_base_host
+    for n in list(range(0, 3000, 97)) + [2999]:
+        classes = sorted(set(hard[n].tolist()))
+        seg = slice(ent_off[n], ent_off[n + 1])
+        assert ent_cls[seg].tolist() == classes                           # one entry per distinct class, ascending
+        for c, pid in zip(classes, ent_pair[seg].tolist()):
+            members = np.nonzero(hard[n] == c)[0]
+            assert pair_cls[pid] == c and base[c] <= pid < base[c + 1]
+            bits = [h for h in range(e.H) if (zmask[pid, h >> 5] >> (h & 31)) & 1]
+            assert bits == members.tolist()
+            if len(members) == 1:
+                assert pid == base[c] + 1 + members[0]                    # singleton template
+            else:
+                assert pid >= base[c] + 1 + e.H and int(e.pair_item[pid]) == n
+    assert int((e.pair_item >= 0).sum()) == e.n_heavy
+
+
+def test_fixed_point_sums_are_shard_invariant():
+    """The sufficient statistics exchanged between GPUs (coda.py:42 sums, coda.py:232 sums) are int64 fixed point:
+    accumulating two half-slabs gives bit-identical results to one pass (through the raw C ABI)."""
+    from coda_b200 import _native as nat
+    from coda_b200.synth import synth
+    lib = nat.load()
+    H, N, C = 16, 5000, 7
+    preds, _ = synth(H, N, C, seed=9)
+    dev = torch.device("cuda:0")
+    P = preds.to(dev)
+    st = torch.cuda.current_stream().cuda_stream
+
+    def conf(p):
+        n = p.shape[1]
+        hard = torch.empty((n, H), dtype=torch.int16, device=dev)
+        pseudo = torch.empty(n, dtype=torch.int32, device=dev)
+        dis = torch.empty(n, dtype=torch.uint8, device=dev)
+        flags = torch.zeros(1, dtype=torch.int32, device=dev)
+        out = torch.zeros((H, C, C), dtype=torch.int64, device=dev)
+        nat.check(lib.coda_b200_scan_slab(p.data_ptr(), H, n, C, hard.data_ptr(), pseudo.data_ptr(), dis.data_ptr(),
+                                          None, flags.data_ptr(), st))
+        nat.check(lib.coda_b200_confusion_accum(p.data_ptr(), pseudo.data_ptr(), H, n, C, 40, out.data_ptr(), st))
+        return out, pseudo
+    whole, pseudo = conf(P)
+    a, _ = conf(P[:, :2300].contiguous())
+    b, _ = conf(P[:, 2300:].contiguous())
+    assert torch.equal(whole, a + b)
+    ref = torch.einsum("nc,hnj->hcj", torch.nn.functional.one_hot(pseudo.long().cpu(), C).float(), preds)
+    np.testing.assert_allclose((whole.double() / 2 ** 40).cpu().numpy(), ref.numpy(), rtol=2e-6, atol=1e-6)
+
+
+def test_api_and_error_behaviour():
+    from coda_b200 import CODA, TensorDataset
+    from coda_b200.synth import synth
+    preds, labels = synth(8, 300, 5, seed=1)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        CODA(TensorDataset(preds, labels))                       # CPU tensor: refuse loudly, never fall back
+    sel = _mk(preds, labels, q="bogus")
+    with pytest.raises(NotImplementedError):                     # coda.py:297
+        sel.get_next_item_to_label()
+    sel = _mk(preds, labels)
+    idx, q = sel.get_next_item_to_label()
+    sel.add_label(idx, int(labels[idx]), q)
+    with pytest.raises(ValueError):                              # coda.py:323 list.remove
+        sel.add_label(idx, int(labels[idx]), q)
+    sel.unlabeled_idxs.remove(5)                                 # demo/app.py:188: skip an item without labeling it
+    for _ in range(3):
+        i2, q2 = sel.get_next_item_to_label()
+        assert i2 not in (idx, 5)
+        sel.add_label(i2, int(labels[i2]), q2)
+    assert len(sel.unlabeled_idxs) == 300 - 5 and 5 not in sel.unlabeled_idxs
+    bad = preds.clone()
+    bad[3, 17, 2] = float("nan")
+    with pytest.raises(RuntimeError, match="NUMERIC ERROR"):     # util.py:20-25
+        _mk(bad, labels)
+    with pytest.raises(ValueError, match="post-softmax"):
+        _mk(preds * 3.0, labels)
+
+    class A:  # coda.py:205-213
+        prefilter_n = 0; alpha = 0.9; learning_rate = 0.01; multiplier = 2.0; no_diag_prior = False; q = "eig"
+    s2 = CODA.from_args(TensorDataset(preds.cuda(), labels.cuda()), A)
+    assert s2.get_next_item_to_label()[0] == _mk(preds, labels).get_next_item_to_label()[0]
+
+
+def test_prefilter_n_subsample_path():
+    """coda.py:221-223 (--prefilter-n): same RNG consumption and pick as the oracle on the subsample."""
+    from coda_b200.synth import synth
+    preds, labels = synth(10, 600, 6, seed=8)
+    random.seed(5)
+    ora = coda_oracle.OracleSelector(preds, prefilter_n=50)
+    i_ref, q_ref = ora.get_next_item_to_label()
+    state_ref = random.getstate()
+    random.seed(5)
+    sel = _mk(preds, labels, prefilter_n=50)
+    i, q = sel.get_next_item_to_label()
+    assert i == i_ref and abs(q - q_ref) < EIG_ATOL and random.getstate() == state_ref and sel.stochastic

@@ -43,8 +43,8 @@ METRIC = "acquisition steps/sec (M=256,N=1e6,C=100)"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=500)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--mode", default="incremental", choices=["incremental", "recompute", "recompute_all"])
@@ -290,9 +290,9 @@ def main():
     value = args.steps / (ms / 1e3)
 
     # per-kernel shares over a few fully instrumented steps (not part of `value`)
-    _, _, prof_all, _ = device_loop(sel, 0, min(10, args.steps), profile_only=[])
+    _, _, prof_all, _ = device_loop(sel, 0, min(20, args.steps), profile_only=[])
 
-    e2e_steps = args.e2e_steps or args.steps
+    e2e_steps = args.e2e_steps or min(args.steps, 200)
     ms_e2e, picks_api = api_loop(sel, max(1, min(args.warmup, 3)), e2e_steps)
     e2e = e2e_steps / (ms_e2e / 1e3)
     h2d = eng.sel_host.numel() * 8
@@ -349,7 +349,7 @@ def main():
                 "mode": args.mode, "l2": "per-step working set (slab gather + row cache + U) >> 126 MB L2; no flush needed",
                 "tie_rule_value": "lowest index (device loop)", "tie_rule_e2e": "random.choice (coda.py:308)",
                 "pairs": npairs, "heavy_pairs": eng.n_heavy, "entries_per_item": eng.n_entries / max(1, n_loc),
-                "gen_s": t_gen, "init_s": t_init,
+                "gen_s": t_gen, "init_s": t_init, "shadow_models": eng.n_shadow,
             },
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": "steps/s", "ms_per_step": ms_e2e / e2e_steps, "h2d_bytes_per_step": h2d,

@@ -40,15 +40,17 @@ SIGNATURES = {
     "coda_b200_pi_reduce": (i32, [p, i64, i32, i32, p, p, p, p]),
     "coda_b200_label_row": (i32, [p, i32, i64, p, p, p, p]),
     "coda_b200_label_apply": (i32, [p, i32, i32, p, p, f64, p]),
-    "coda_b200_pi_rank1": (i32, [p, p, i32, i64, i32, p, p, f64, i32, p, p, p, p, p]),
+    "coda_b200_pi_rank1": (i32, [p, p, p, p, i32, i64, i32, p, p, f64, i32, p, p, p, p, i32, p]),
+    "coda_b200_shadow_build": (i32, [p, i32, i64, i32, p, i32, p, p]),
     "coda_b200_set_l2_fetch_granularity": (i32, [i32]),
     "coda_b200_tables_scratch_bytes": (sz, [i32, i32]),
-    "coda_b200_beta_tables": (i32, [p, p, i32, i32, i32, f64, i32, i32, p, p, p, p, p, p, p, p]),
+    "coda_b200_beta_tables": (i32, [p, p, i32, i32, i32, f64, i32, i32, p, p, p, p, p, p, p, p, p, p]),
+    "coda_b200_pair_rows_tc": (i32, [p, i32, i32, p, p, p, p, p, p, i32, p, p, p, p, p, p]),
     "coda_b200_mixture": (i32, [p, p, i32, i32, p, p, p, p, p, p]),
     "coda_b200_pair_count": (i32, [p, i32, i64, i32, p, p, p]),
     "coda_b200_pair_fill": (i32, [p, i32, i64, i32, p, p, p, p, p, p, p, p, p]),
     "coda_b200_pair_rows": (i32, [p, i32, i32, p, p, p, p, p, p, p, i32, p, p, p, p, p, p]),
-    "coda_b200_pair_gain": (i32, [p, p, i64, i32, p, p, p, p, p]),
+    "coda_b200_pair_gain": (i32, [p, p, i64, i32, p, p, p, p, p, p, i32, i32, p]),
     "coda_b200_eig_blocks": (i32, [i64]),
     "coda_b200_eig_points": (i32, [p, i64, i32, p, p, p, p, p, p, p, i64, p, p, p, p]),
     "coda_b200_select_merge": (i32, [p, i32, p, p]),

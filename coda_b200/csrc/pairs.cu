@@ -455,8 +455,19 @@ __global__ void __launch_bounds__(256) k_pair_gain_fast(const float* __restrict_
                                                         const uint16_t* __restrict__ pair_cls, long long npairs,
                                                         int H, const float* __restrict__ PB,
                                                         const float* __restrict__ m0,
-                                                        const float* __restrict__ pi_hat, float* __restrict__ gain) {
+                                                        const float* __restrict__ pi_hat, float* __restrict__ gain,
+                                                        const long long* __restrict__ sel,
+                                                        const long long* __restrict__ cls_base, int cls_host,
+                                                        int filter) {
   constexpr int Hp = 128 * NQ;
+  // filter: 0 = every pair, 1 = every pair except class t, 2 = only class t; t = sel[1] (device) or cls_host
+  long long skip_lo = -1, skip_hi = -1, base0 = 0, total = npairs;
+  if (filter) {
+    const long long t = sel ? sel[1] : cls_host;
+    const long long lo = cls_base[t], hi = cls_base[t + 1];
+    if (filter == 1) { skip_lo = lo; skip_hi = hi; }
+    else { base0 = lo; total = hi - lo; }
+  }
   constexpr int CH = 32;   // pairs per warp chunk
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float4 m[NQ], fm[NQ], pb[NQ];
@@ -474,10 +485,11 @@ __global__ void __launch_bounds__(256) k_pair_gain_fast(const float* __restrict_
   }
   int cur = -1;
   float pic = 0.f;
-  const long long nchunks = (npairs + CH - 1) / CH;
+  const long long nchunks = (total + CH - 1) / CH;
   for (long long ch = (long long)blockIdx.x * 8 + warp; ch < nchunks; ch += (long long)gridDim.x * 8) {
-    const long long p0 = ch * CH;
-    const long long p1 = min(npairs, p0 + CH);
+    const long long p0 = base0 + ch * CH;
+    const long long p1 = min(base0 + total, p0 + CH);
+    if (p0 >= skip_lo && p1 <= skip_hi) continue;          // chunk entirely inside the excluded class
     for (long long i = p0; i < p1; i += 4) {
       float4 a[4][NQ];
 #pragma unroll
@@ -490,7 +502,7 @@ __global__ void __launch_bounds__(256) k_pair_gain_fast(const float* __restrict_
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const long long pid = i + j;
-        if (pid < p1) {
+        if (pid < p1 && !(pid >= skip_lo && pid < skip_hi)) {
           const int c = pair_cls[pid];
           if (c != cur) {
             cur = c;
@@ -511,20 +523,27 @@ __global__ void __launch_bounds__(256) k_pair_gain_fast(const float* __restrict_
 
 extern "C" int coda_b200_pair_gain(const float* ph_cache, const uint16_t* pair_cls, int64_t npairs, int H,
                                    const float* PB, const float* m0, const float* pi_hat, float* gain,
+                                   const int64_t* sel, const int64_t* cls_base, int cls_host, int filter,
                                    coda_stream_t stream) {
   CODA_CHECK_ARG(ph_cache && pair_cls && PB && m0 && pi_hat && gain, "pair_gain: null pointer");
+  CODA_CHECK_ARG(filter >= 0 && filter <= 2 && (!filter || cls_base), "pair_gain: bad filter");
   const int Hp = (H + 31) / 32 * 32;
   cudaStream_t st = as_stream(stream);
+  const long long* seld = reinterpret_cast<const long long*>(sel);
+  const long long* cb = reinterpret_cast<const long long*>(cls_base);
   if (Hp % 128 == 0 && Hp <= 512) {
     int grid = (int)min((long long)(npairs + 255) / 256, (long long)coda_sm_count() * 6);
     if (grid < 1) grid = 1;
-    if (Hp == 128) k_pair_gain_fast<1><<<grid, 256, 0, st>>>(ph_cache, pair_cls, npairs, H, PB, m0, pi_hat, gain);
-    else if (Hp == 256) k_pair_gain_fast<2><<<grid, 256, 0, st>>>(ph_cache, pair_cls, npairs, H, PB, m0, pi_hat, gain);
-    else if (Hp == 384) k_pair_gain_fast<3><<<grid, 256, 0, st>>>(ph_cache, pair_cls, npairs, H, PB, m0, pi_hat, gain);
-    else k_pair_gain_fast<4><<<grid, 256, 0, st>>>(ph_cache, pair_cls, npairs, H, PB, m0, pi_hat, gain);
+#define LAUNCH_PG(NQ) k_pair_gain_fast<NQ><<<grid, 256, 0, st>>>(ph_cache, pair_cls, npairs, H, PB, m0, pi_hat, gain, seld, cb, cls_host, filter)
+    if (Hp == 128) LAUNCH_PG(1);
+    else if (Hp == 256) LAUNCH_PG(2);
+    else if (Hp == 384) LAUNCH_PG(3);
+    else LAUNCH_PG(4);
+#undef LAUNCH_PG
     CODA_LAUNCH_OK("k_pair_gain_fast");
     return CODA_B200_OK;
   }
+  if (filter == 1) return CODA_B200_OK;   // generic path: one full pass when called with filter 2 (or 0)
   size_t smem = (size_t)2 * Hp * 4;
   int grid = (int)min((long long)(npairs + 15) / 16, (long long)coda_sm_count() * 8);
   if (grid < 1) grid = 1;

@@ -51,84 +51,80 @@ __global__ void __launch_bounds__(256) k_eig_points(const float* __restrict__ U,
   Best bA{-INFINITY, IDX_NONE}, bB{-INFINITY, IDX_NONE};
   long long cntA = 0;
   uint32_t bad = 0;
-  // software pipeline over the items of this warp: the row, CSR bounds and first 32 entries of item n+stride
-  // are in flight while item n is reduced, so only the gain gather is exposed per iteration.
+  // IT items per warp iteration: all row / CSR-bound loads first, then the entry loads, then the gain
+  // gathers, so each dependent level costs one memory latency for IT items instead of one.
+  constexpr int IT = 4;
+  constexpr int KR = KC > 0 ? KC : 1;
   const long long stride = (long long)gridDim.x * 8;
-  long long n = (long long)blockIdx.x * 8 + warp;
-  float u[KC > 0 ? KC : 1];
-  long long o0 = 0, o1 = 0;
-  int ec = -1, ep = 0;
-  auto load_row = [&](long long nn, float (&dst)[KC > 0 ? KC : 1]) {
-    if (KC > 0) {
-      const float* r = U + (size_t)nn * C;
+  for (long long nb = ((long long)blockIdx.x * 8 + warp) * IT; nb < N; nb += stride * IT) {
+    float u[IT][KR];
+    long long o0[IT], o1[IT];
 #pragma unroll
-      for (int k = 0; k < (KC > 0 ? KC : 1); ++k) {
-        const int c = lane + 32 * k;
-        dst[k] = c < C ? __ldg(r + c) : 0.f;
-      }
-    }
-  };
-  if (n < N) {
-    load_row(n, u);
-    o0 = __ldg(ent_off + n);
-    o1 = __ldg(ent_off + n + 1);
-    if (o0 + lane < o1) { ec = ent_cls[o0 + lane]; ep = ent_pair[o0 + lane]; }
-  }
-  while (n < N) {
-    const long long nn = n + stride;
-    const float* urow = U + (size_t)n * C;
-    float un[KC > 0 ? KC : 1];
-    long long o0n = 0, o1n = 0;
-    if (nn < N) {
-      load_row(nn, un);
-      o0n = __ldg(ent_off + nn);
-      o1n = __ldg(ent_off + nn + 1);
-    }
-    float eg = 0.f, eu = 0.f;
-    if (ec >= 0) { eg = __ldg(gain + ep); eu = __ldg(urow + ec); }
-    float s = 0.f, e = 0.f;
-    if (KC > 0) {
+    for (int i = 0; i < IT; ++i) {
+      const long long n = min(nb + i, N - 1);
+      if (KC > 0) {
 #pragma unroll
-      for (int k = 0; k < (KC > 0 ? KC : 1); ++k) {
-        const int c = lane + 32 * k;
-        s += u[k];
-        if (c < C) e = fmaf(u[k], g0[c], e);
-      }
-    } else {
-      for (int c = lane; c < C; c += 32) {
-        const float v = __ldg(urow + c);
-        s += v;
-        e = fmaf(v, g0[c], e);
-      }
-    }
-    if (ec >= 0) e = fmaf(eu, eg - g0[ec], e);
-    for (long long k0 = o0 + lane + 32; k0 < o1; k0 += 32) {   // items with more than 32 distinct predicted classes
-      const int c = ent_cls[k0];
-      e = fmaf(__ldg(urow + c), __ldg(gain + ent_pair[k0]) - g0[c], e);
-    }
-    // next item's entries (their addresses depend on o0n, which has had the reductions above to arrive)
-    int ecn = -1, epn = 0;
-    if (nn < N && o0n + lane < o1n) { ecn = ent_cls[o0n + lane]; epn = ent_pair[o0n + lane]; }
-    s = warp_sum(s);
-    e = warp_sum(e);
-    if (lane == 0) {
-      // eig = sum_c xi_c * gain_c with xi = U / max(sum U, 1e-12) (coda.py:230, 278): one division per item
-      const float v = e / fmaxf(s, 1e-12f);
-      eig[n] = v;
-      if (!isfinite(v)) bad |= CODA_B200_FLAG_NONFINITE_EIG;
-      if (!labeled[n]) {
-        best_update(bB, v, n_offset + n);
-        if (disagree[n]) {
-          best_update(bA, v, n_offset + n);
-          ++cntA;
+        for (int k = 0; k < KR; ++k) {
+          const int c = lane + 32 * k;
+          u[i][k] = c < C ? __ldg(U + (size_t)n * C + c) : 0.f;
         }
       }
+      o0[i] = __ldg(ent_off + n);
+      o1[i] = __ldg(ent_off + n + 1);
     }
-    n = nn;
-    o0 = o0n; o1 = o1n; ec = ecn; ep = epn;
-    if (KC > 0) {
+    int ec[IT], ep[IT];
 #pragma unroll
-      for (int k = 0; k < (KC > 0 ? KC : 1); ++k) u[k] = un[k];
+    for (int i = 0; i < IT; ++i) {
+      ec[i] = -1; ep[i] = 0;
+      if (o0[i] + lane < o1[i]) { ec[i] = ent_cls[o0[i] + lane]; ep[i] = ent_pair[o0[i] + lane]; }
+    }
+    float eg[IT], eu[IT];
+#pragma unroll
+    for (int i = 0; i < IT; ++i) {
+      const long long n = min(nb + i, N - 1);
+      eg[i] = 0.f; eu[i] = 0.f;
+      if (ec[i] >= 0) { eg[i] = __ldg(gain + ep[i]); eu[i] = __ldg(U + (size_t)n * C + ec[i]); }
+    }
+#pragma unroll
+    for (int i = 0; i < IT; ++i) {
+      const long long n = nb + i;
+      if (n >= N) break;
+      const float* urow = U + (size_t)n * C;
+      float s = 0.f, e = 0.f;
+      if (KC > 0) {
+#pragma unroll
+        for (int k = 0; k < KR; ++k) {
+          const int c = lane + 32 * k;
+          s += u[i][k];
+          if (c < C) e = fmaf(u[i][k], g0[c], e);
+        }
+      } else {
+        for (int c = lane; c < C; c += 32) {
+          const float v = __ldg(urow + c);
+          s += v;
+          e = fmaf(v, g0[c], e);
+        }
+      }
+      if (ec[i] >= 0) e = fmaf(eu[i], eg[i] - g0[ec[i]], e);
+      for (long long k0 = o0[i] + lane + 32; k0 < o1[i]; k0 += 32) {   // > 32 distinct predicted classes
+        const int c = ent_cls[k0];
+        e = fmaf(__ldg(urow + c), __ldg(gain + ent_pair[k0]) - g0[c], e);
+      }
+      s = warp_sum(s);
+      e = warp_sum(e);
+      if (lane == 0) {
+        // eig = sum_c xi_c * gain_c with xi = U / max(sum U, 1e-12) (coda.py:230, 278): one division per item
+        const float v = e / fmaxf(s, 1e-12f);
+        eig[n] = v;
+        if (!isfinite(v)) bad |= CODA_B200_FLAG_NONFINITE_EIG;
+        if (!labeled[n]) {
+          best_update(bB, v, n_offset + n);
+          if (disagree[n]) {
+            best_update(bA, v, n_offset + n);
+            ++cntA;
+          }
+        }
+      }
     }
   }
   if (lane == 0) {
@@ -151,8 +147,8 @@ __global__ void __launch_bounds__(256) k_eig_points(const float* __restrict__ U,
 }
 
 extern "C" int coda_b200_eig_blocks(int64_t N) {
-  long long want = (N + 7) / 8;
-  long long cap = (long long)coda_sm_count() * 16;
+  long long want = (N + 31) / 32;
+  long long cap = (long long)coda_sm_count() * 8;
   return (int)(want < cap ? (want < 1 ? 1 : want) : cap);
 }
 

@@ -368,21 +368,62 @@ extern "C" int coda_b200_label_apply(float* D, int H, int C, const int64_t* sel,
   return CODA_B200_OK;
 }
 
-// label_terms: turn jvec into the list of (sign, element offset) gathers pi_rank1 performs.
+// ---------------------------------------------------------------------------------------
+// class-major shadow copy  T[s][c][n] = preds[h_s][n][c]  for a subset of models (as many as spare HBM
+// allows, least accurate first).  The rank-1 refresh needs ONE float per (model, item): from the reference
+// layout that costs a 64-byte DRAM fetch each, from the shadow it is a coalesced 4-byte read.
+// grid = (ceil(N/32), ceil(C/32), S), block = (32, 8)
+// ---------------------------------------------------------------------------------------
+__global__ void k_shadow_transpose(const float* __restrict__ preds, long long N, int C,
+                                   const int32_t* __restrict__ model_of_slot, float* __restrict__ T) {
+  __shared__ float tile[32][33];
+  const int s = blockIdx.z, h = model_of_slot[s];
+  const long long n0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const float* src = preds + (size_t)h * N * C;
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const long long n = n0 + r;
+    const int c = c0 + threadIdx.x;
+    tile[r][threadIdx.x] = (n < N && c < C) ? __ldg(src + (size_t)n * C + c) : 0.f;
+  }
+  __syncthreads();
+  float* dst = T + (size_t)s * C * N;
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int c = c0 + r;
+    const long long n = n0 + threadIdx.x;
+    if (c < C && n < N) dst[(size_t)c * N + n] = tile[threadIdx.x][r];
+  }
+}
+
+extern "C" int coda_b200_shadow_build(const float* preds, int H, int64_t N, int C, const int32_t* model_of_slot, int S,
+                                      float* T, coda_stream_t stream) {
+  CODA_CHECK_ARG(preds && model_of_slot && T && S >= 1 && S <= H, "shadow_build: bad arguments");
+  long long gx = (N + 31) / 32;
+  CODA_CHECK_ARG(gx <= 0x7fffffffLL && S <= 65535, "shadow_build: grid too large");
+  dim3 grid((unsigned)gx, (unsigned)((C + 31) / 32), (unsigned)S), block(32, 8);
+  k_shadow_transpose<<<grid, block, 0, as_stream(stream)>>>(preds, N, C, model_of_slot, T);
+  CODA_LAUNCH_OK("k_shadow_transpose");
+  return CODA_B200_OK;
+}
+
+// label_terms: turn jvec into the list of (sign, element offset, item stride) gathers pi_rank1 performs.
 //   direct     : sum_h preds[h][n][j_h]                                  -> H terms
 //   ensemble   : with t' = the most common j_h and E[n][c] = sum_h preds[h][n][c],
 //                sum_h preds[h][n][j_h] = E[n][t'] + sum_{h: j_h != t'} (preds[h][n][j_h] - preds[h][n][t'])
-//                -> 2*M terms (M = models that disagree with the majority on the labeled item); both
-//                elements of a disagreeing model sit in the same 400-byte row, usually the same line.
+//                -> 2*M terms (M = models that disagree with the majority on the labeled item).
+// A model with a shadow slot is read from T (item stride 1) instead of preds (item stride C).
 // hdr = {nterms, t' or -1}.  The term table is then copied into __constant__ memory so that the gather
 // loop reads it through the uniform/constant path instead of the LSU.
 #define R1_MAXT 2048
-__constant__ long long c_toff[R1_MAXT];
+__constant__ long long c_toff[R1_MAXT];   // element offset relative to preds for item 0
 __constant__ float c_tsg[R1_MAXT];
+__constant__ int c_tstr[R1_MAXT];         // element stride per item: C (reference layout) or 1 (shadow)
 
-__global__ void __launch_bounds__(256) k_label_terms(const int32_t* __restrict__ jvec, int H, int C, long long hstride,
-                                                     int have_ens, int32_t* __restrict__ hdr,
-                                                     long long* __restrict__ toff, float* __restrict__ tsg) {
+__global__ void __launch_bounds__(256) k_label_terms(const int32_t* __restrict__ jvec, int H, int C, long long N,
+                                                     int have_ens, const int32_t* __restrict__ slot_of_model,
+                                                     long long shadow_off, int32_t* __restrict__ hdr,
+                                                     long long* __restrict__ toff, float* __restrict__ tsg,
+                                                     int* __restrict__ tstr) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int* cnt = reinterpret_cast<int*>(smem_raw);   // [C]
   __shared__ int s_tp, s_m;
@@ -402,13 +443,25 @@ __global__ void __launch_bounds__(256) k_label_terms(const int32_t* __restrict__
   const bool ens = have_ens && 2 * M < H;
   if (threadIdx.x == 0) {
     int k = 0;
+    auto emit = [&](int h, int j, float sign) {
+      const int slot = slot_of_model ? slot_of_model[h] : -1;
+      if (slot >= 0) {
+        toff[k] = shadow_off + ((long long)slot * C + j) * N;
+        tstr[k] = 1;
+      } else {
+        toff[k] = (long long)h * N * C + j;
+        tstr[k] = C;
+      }
+      tsg[k] = sign;
+      ++k;
+    };
     for (int h = 0; h < H; ++h) {
       const int j = jvec[h];
       if (!ens) {
-        toff[k] = (long long)h * hstride + j; tsg[k] = 1.f; ++k;
+        emit(h, j, 1.f);
       } else if (j != tp) {
-        toff[k] = (long long)h * hstride + j; tsg[k] = 1.f; ++k;
-        toff[k] = (long long)h * hstride + tp; tsg[k] = -1.f; ++k;
+        emit(h, j, 1.f);
+        emit(h, tp, -1.f);
       }
     }
     hdr[0] = k;
@@ -436,17 +489,16 @@ __global__ void __launch_bounds__(256) k_pi_rank1(const float* __restrict__ pred
     const long long n = n0 + threadIdx.x;
     float d = 0.f;
     if (n < N) {
-      const float* p = preds + (size_t)n * C;
       if (tp >= 0) d = __ldg(E + (size_t)n * C + tp);
       int k = 0;
       for (; k + 8 <= nt; k += 8) {
         float v[8];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) v[q] = __ldg(p + c_toff[k + q]);
+        for (int q = 0; q < 8; ++q) v[q] = __ldg(preds + c_toff[k + q] + n * c_tstr[k + q]);
 #pragma unroll
         for (int q = 0; q < 8; ++q) d = fmaf(c_tsg[k + q], v[q], d);
       }
-      for (; k < nt; ++k) d = fmaf(c_tsg[k], __ldg(p + c_toff[k]), d);
+      for (; k < nt; ++k) d = fmaf(c_tsg[k], __ldg(preds + c_toff[k] + n * c_tstr[k]), d);
     }
     delta[threadIdx.x] = lr * d;
     __syncthreads();
@@ -463,29 +515,37 @@ __global__ void __launch_bounds__(256) k_pi_rank1(const float* __restrict__ pred
   if (bad) atomicOr(flags, bad);
 }
 
-extern "C" int coda_b200_pi_rank1(const float* preds, const float* ens, int H, int64_t N, int C, const int64_t* sel,
-                                  const int32_t* jvec, double lr, int fx_shift, int32_t* terms /*[2 + 6H]*/, float* U,
-                                  int64_t* pisum_fx, uint32_t* flags, coda_stream_t stream) {
+extern "C" int coda_b200_pi_rank1(const float* preds, const float* ens, const float* shadow,
+                                  const int32_t* slot_of_model, int H, int64_t N, int C, const int64_t* sel,
+                                  const int32_t* jvec, double lr, int fx_shift, int32_t* terms /*[2 + 8H]*/, float* U,
+                                  int64_t* pisum_fx, uint32_t* flags, int ctas_per_sm, coda_stream_t stream) {
   CODA_CHECK_ARG(preds && sel && jvec && terms && U && pisum_fx && flags, "pi_rank1: null pointer");
   CODA_CHECK_ARG(2 * H <= R1_MAXT, "pi_rank1: H=%d too large", H);
   CODA_CHECK_ARG((reinterpret_cast<uintptr_t>(terms) & 7) == 0, "pi_rank1: terms must be 8-byte aligned");
+  CODA_CHECK_ARG(!shadow || slot_of_model, "pi_rank1: shadow needs slot_of_model");
   int32_t* hdr = terms;                                            // 2 ints
   long long* toff = reinterpret_cast<long long*>(terms + 2);       // 2H int64
   float* tsg = reinterpret_cast<float*>(toff + 2 * H);             // 2H floats
+  int* tstr = reinterpret_cast<int*>(tsg + 2 * H);                 // 2H ints
   CODA_CHECK_ARG((size_t)C * 4 <= 48 * 1024, "pi_rank1: C=%d too large", C);
   cudaStream_t st = as_stream(stream);
-  k_label_terms<<<1, 256, (size_t)C * 4, st>>>(jvec, H, C, (long long)N * C, ens != nullptr, hdr, toff, tsg);
+  const long long shadow_off = shadow ? (long long)(shadow - preds) : 0;   // both 4-byte aligned device pointers
+  k_label_terms<<<1, 256, (size_t)C * 4, st>>>(jvec, H, C, (long long)N, ens != nullptr,
+                                                shadow ? slot_of_model : nullptr, shadow_off, hdr, toff, tsg, tstr);
   CODA_LAUNCH_OK("k_label_terms");
-  void *d_toff = nullptr, *d_tsg = nullptr;
+  void *d_toff = nullptr, *d_tsg = nullptr, *d_tstr = nullptr;
   CODA_CUDA_OK(cudaGetSymbolAddress(&d_toff, c_toff));
   CODA_CUDA_OK(cudaGetSymbolAddress(&d_tsg, c_tsg));
+  CODA_CUDA_OK(cudaGetSymbolAddress(&d_tstr, c_tstr));
   CODA_CUDA_OK(cudaMemcpyAsync(d_toff, toff, (size_t)2 * H * 8, cudaMemcpyDeviceToDevice, st));
   CODA_CUDA_OK(cudaMemcpyAsync(d_tsg, tsg, (size_t)2 * H * 4, cudaMemcpyDeviceToDevice, st));
+  CODA_CUDA_OK(cudaMemcpyAsync(d_tstr, tstr, (size_t)2 * H * 4, cudaMemcpyDeviceToDevice, st));
   size_t smem = (size_t)8 * C * 8 + R1_TN * 4;
   CODA_CHECK_ARG(smem <= 200 * 1024, "pi_rank1: C=%d too large", C);
   CODA_CUDA_OK(cudaFuncSetAttribute(k_pi_rank1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   long long want = (N + R1_TN - 1) / R1_TN;
-  int grid = (int)min(want, (long long)coda_sm_count() * 8);
+  if (ctas_per_sm < 1 || ctas_per_sm > 8) ctas_per_sm = 8;
+  int grid = (int)min(want, (long long)coda_sm_count() * ctas_per_sm);
   k_pi_rank1<<<grid, 256, smem, st>>>(preds, ens, N, C, reinterpret_cast<const long long*>(sel), hdr, (float)lr,
                                       exp2f((float)fx_shift), U, reinterpret_cast<unsigned long long*>(pisum_fx), flags);
   CODA_LAUNCH_OK("k_pi_rank1");

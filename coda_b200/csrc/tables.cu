@@ -20,6 +20,8 @@
 // Tables are built in fp64 from fp32 inputs and rounded to fp32 once.
 #include "common.cuh"
 
+#include <cuda_bf16.h>
+
 #define TP_ 256   // quadrature nodes == threads per block in the table kernels
 
 __device__ __forceinline__ double block_scan_incl(double v, double* wsum /*[8]*/) {
@@ -95,6 +97,7 @@ __global__ void __launch_bounds__(TP_) k_beta_combine(const double* __restrict__
                                                       const float* __restrict__ grid_x, int H, int Hp, int cls_lo,
                                                       const long long* __restrict__ sel, float* __restrict__ dL,
                                                       float* __restrict__ G0T, float* __restrict__ G1T,
+                                                      __nv_bfloat16* __restrict__ dLb, __nv_bfloat16* __restrict__ Gb,
                                                       double* __restrict__ pb_raw, uint32_t* __restrict__ flags) {
   if (sel) cls_lo = (int)sel[1];
   __shared__ double part[8];
@@ -126,9 +129,34 @@ __global__ void __launch_bounds__(TP_) k_beta_combine(const double* __restrict__
     double ib = wq * pb[o] * exp(fmin(fmax(SB - lb, -80.0), 80.0));
     const float g0f = (float)g0, g1f = (float)g1;
     if (!isfinite(g0f) || !isfinite(g1f) || !isfinite(ib)) bad |= CODA_B200_FLAG_NONFINITE_TABLE;
-    dL[((size_t)c * H + h) * TP_ + x] = (float)(lh - lm);
+    const float dlf = (float)(lh - lm);
+    dL[((size_t)c * H + h) * TP_ + x] = dlf;
     G0T[((size_t)c * TP_ + x) * Hp + h] = g0f;
     G1T[((size_t)c * TP_ + x) * Hp + h] = g1f;
+    if (dLb) {
+      // tensor-core operand tables (pairs_tc.cu): bf16 limbs in the UMMA no-swizzle K-major core-matrix order
+      // [k_core][r_core][8 rows][8 elements].  dLb tile: rows = nodes, K = 32 models; Gb tile: rows = models, K = 16 nodes.
+      const __nv_bfloat16 d0 = __float2bfloat16_rn(dlf);
+      const float r1 = dlf - __bfloat162float(d0);
+      const __nv_bfloat16 d1 = __float2bfloat16_rn(r1);
+      const __nv_bfloat16 d2 = __float2bfloat16_rn(r1 - __bfloat162float(d1));
+      const size_t nka = (size_t)Hp / 32;
+      const size_t ta = ((size_t)c * nka + (h >> 5)) * 3 * (TP_ * 32);
+      const size_t ea = (size_t)((((h & 31) >> 3) * (TP_ / 8) + (x >> 3)) * 64 + (x & 7) * 8 + (h & 7));
+      dLb[ta + 0 * (TP_ * 32) + ea] = d0;
+      dLb[ta + 1 * (TP_ * 32) + ea] = d1;
+      dLb[ta + 2 * (TP_ * 32) + ea] = d2;
+      const __nv_bfloat16 a0 = __float2bfloat16_rn(g0f), b0 = __float2bfloat16_rn(g1f);
+      const __nv_bfloat16 a1 = __float2bfloat16_rn(g0f - __bfloat162float(a0));
+      const __nv_bfloat16 b1 = __float2bfloat16_rn(g1f - __bfloat162float(b0));
+      const size_t tsz = (size_t)Hp * 16;
+      const size_t tb = ((size_t)c * (TP_ / 16) + (x >> 4)) * 4 * tsz;
+      const size_t eb = (size_t)((((x & 15) >> 3) * (Hp / 8) + (h >> 3)) * 64 + (h & 7) * 8 + (x & 7));
+      Gb[tb + 0 * tsz + eb] = a0;
+      Gb[tb + 1 * tsz + eb] = a1;
+      Gb[tb + 2 * tsz + eb] = b0;
+      Gb[tb + 3 * tsz + eb] = b1;
+    }
     ib = warp_sum(ib);
     __syncthreads();
     if (lane == 0) part[warp] = ib;
@@ -169,9 +197,11 @@ extern "C" size_t coda_b200_tables_scratch_bytes(int H, int ncls) {
 
 extern "C" int coda_b200_beta_tables(const float* D, const float* grid_x, int H, int C, int P, double hyp_w,
                                      int cls_lo, int cls_hi, const int64_t* sel, void* scratch, float* dL,
-                                     float* G0T, float* G1T, float* PB, uint32_t* flags, coda_stream_t stream) {
+                                     float* G0T, float* G1T, float* PB, void* dLb, void* Gb, uint32_t* flags,
+                                     coda_stream_t stream) {
   CODA_CHECK_ARG(D && grid_x && scratch && dL && G0T && G1T && PB && flags, "beta_tables: null pointer");
   CODA_CHECK_ARG(P == TP_, "beta_tables: P must be %d", TP_);
+  CODA_CHECK_ARG((dLb == nullptr) == (Gb == nullptr), "beta_tables: dLb and Gb go together");
   if (sel) { cls_lo = 0; cls_hi = 1; }   // one class, index read from sel[1] on the device
   CODA_CHECK_ARG(0 <= cls_lo && cls_lo < cls_hi && cls_hi <= C, "beta_tables: bad class range [%d,%d)", cls_lo, cls_hi);
   const int ncls = cls_hi - cls_lo;
@@ -184,7 +214,8 @@ extern "C" int coda_b200_beta_tables(const float* D, const float* grid_x, int H,
   k_beta_nodes<<<g1, TP_, 0, as_stream(stream)>>>(D, grid_x, H, C, cls_lo, (float)hyp_w, seld, pdf_s, L_s, flags);
   CODA_LAUNCH_OK("k_beta_nodes");
   dim3 g2((unsigned)ncls, HSPLIT);
-  k_beta_combine<<<g2, TP_, 0, as_stream(stream)>>>(pdf_s, L_s, grid_x, H, Hp, cls_lo, seld, dL, G0T, G1T, pb_raw, flags);
+  k_beta_combine<<<g2, TP_, 0, as_stream(stream)>>>(pdf_s, L_s, grid_x, H, Hp, cls_lo, seld, dL, G0T, G1T,
+                                                    reinterpret_cast<__nv_bfloat16*>(dLb), reinterpret_cast<__nv_bfloat16*>(Gb), pb_raw, flags);
   CODA_LAUNCH_OK("k_beta_combine");
   k_pb_normalize<<<ncls, TP_, 0, as_stream(stream)>>>(pb_raw, H, Hp, cls_lo, seld, PB, flags);
   CODA_LAUNCH_OK("k_pb_normalize");

@@ -70,6 +70,9 @@ class Engine:
             raise NotImplementedError("coda_b200: C > 4096 classes is not supported yet")
         self.fx_shift = max(8, min(40, 62 - math.ceil(math.log2(self.n_global + 1))))
         self.counters = {"launches": 0}
+        # side-stream refresh of the class-t tables/rows concurrently with the marginal pass: measured neutral on
+        # B200 (both kernels want the same SMs), so off by default; CODA_B200_OVERLAP=1 enables it.
+        self.overlap = os.environ.get("CODA_B200_OVERLAP", "0") == "1"
         self.profile, self.profile_only = None, None
         with torch.cuda.device(self.dev):
             self._alloc_static()
@@ -126,6 +129,10 @@ class Engine:
         self.G0T = self._z((C, P, Hp), torch.float32)
         self.G1T = self._z((C, P, Hp), torch.float32)
         self.PB = self._z((C, Hp), torch.float32)
+        # bf16 limb tables in tensor-core operand order (pairs_tc.cu); SIMT kernel (pairs.cu) when Hp > 256
+        self.use_tc = Hp <= 256 and os.environ.get("CODA_B200_TC", "1") != "0"
+        self.dLb = self._z((C, Hp // 32, 3, 256 * 32), torch.bfloat16) if self.use_tc else None
+        self.Gb = self._z((C, 16, 4, Hp * 16), torch.bfloat16) if self.use_tc else None
         self.pi_hat = self._z((C,), torch.float32)
         self.m0 = self._z((Hp,), torch.float32)
         self.hb = self._z((1,), torch.float32)
@@ -144,7 +151,7 @@ class Engine:
         self.sel = self._z((2,), torch.int64)
         self.sel_host = torch.zeros((2,), dtype=torch.int64).pin_memory()
         self.jvec = self._z((H,), torch.int32)
-        self.terms = self._z((2 + 6 * H + 2,), torch.int64).view(torch.int32)[: 2 + 6 * H]   # 8-byte aligned
+        self.terms = self._z((2 + 8 * H + 2,), torch.int64).view(torch.int32)[: 2 + 8 * H]   # 8-byte aligned
         # ensemble sums E[n][c] (N*C floats) feed pi_rank1's majority shortcut; CODA_B200_ENS=0 disables it
         self.ens = self._e((N, C), torch.float32) if os.environ.get("CODA_B200_ENS", "1") != "0" else None
         cls_per_batch = max(1, min(C, TABLE_BATCH_BYTES // max(1, self.lib.coda_b200_tables_scratch_bytes(H, 1))))
@@ -164,11 +171,13 @@ class Engine:
         self.conf_fx = None                                     # H*C*C int64, only needed once
         self._refresh_marginals_full()
         self._build_pairs()
+        self._build_shadow()
         self._tables(0, C)
         self._mixture()
         self.cache_valid = False     # incremental mode: P(best | hypothetical) rows of every pair are cached
         self.side = torch.cuda.Stream(device=self.dev)
-        self.ev_fork, self.ev_join = torch.cuda.Event(), torch.cuda.Event()
+        self.ev_fork, self.ev_join, self.ev_tables = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+        self.pending = None
         self.scored = False
         self.check_flags(sync=True)
 
@@ -199,20 +208,22 @@ class Engine:
             raise NotImplementedError("coda_b200: more than 2^31 pairs in one shard")
         self.cls_base_host = cls_base
         self.cls_base = torch.from_numpy(cls_base).to(self.dev)
-        # tiles of <= 32 same-class pairs
-        nt = (per_cls + 31) // 32
-        tile_off = np.zeros(C + 1, dtype=np.int64)
-        np.cumsum(nt, out=tile_off[1:])
-        cls_of_tile = np.repeat(np.arange(C, dtype=np.int64), nt)
-        k_in_cls = np.arange(int(tile_off[-1]), dtype=np.int64) - tile_off[cls_of_tile]
-        start = cls_base[cls_of_tile] + 32 * k_in_cls
-        cnt = np.minimum(32, per_cls[cls_of_tile] - 32 * k_in_cls)
-        tiles = np.stack([cls_of_tile, start, cnt, np.zeros_like(cnt)], axis=1).astype(np.int32)
+        # tiles of <= 32 (SIMT) or <= 128 (tcgen05) same-class pairs
+        def make_tiles(width):
+            nt = (per_cls + width - 1) // width
+            tile_off = np.zeros(C + 1, dtype=np.int64)
+            np.cumsum(nt, out=tile_off[1:])
+            cls_of_tile = np.repeat(np.arange(C, dtype=np.int64), nt)
+            k_in_cls = np.arange(int(tile_off[-1]), dtype=np.int64) - tile_off[cls_of_tile]
+            start = cls_base[cls_of_tile] + width * k_in_cls
+            cnt = np.minimum(width, per_cls[cls_of_tile] - width * k_in_cls)
+            tiles = np.stack([cls_of_tile, start, cnt, np.zeros_like(cnt)], axis=1).astype(np.int32)
+            return tile_off, int(nt.max()), torch.from_numpy(tiles).to(self.dev)
+        width = 128 if self.use_tc else 32
+        tile_off, self.max_cls_tiles, self.tiles = make_tiles(width)
         self.tile_off_host = tile_off
         self.tile_off = torch.from_numpy(tile_off).to(self.dev)
-        self.max_cls_tiles = int(nt.max())
         self.ntiles = int(tile_off[-1])
-        self.tiles = torch.from_numpy(tiles).to(self.dev)
         self.ent_pair = self._e((max(1, n_ent),), torch.int32)
         self.ent_cls = self._e((max(1, n_ent),), torch.int16)
         self.zmask = self._e((self.npairs, W), torch.int32)
@@ -225,6 +236,36 @@ class Engine:
         self.gain = self._z((self.npairs,), torch.float32)
         self.ph_cache = self._e((self.npairs, self.Hp), torch.float32) if self.mode == "incremental" else None
 
+    def _build_shadow(self):
+        """Class-major shadow copy of as many models as spare HBM allows (least accurate first)."""
+        self.shadow, self.slot_of_model, self.n_shadow = None, None, 0
+        if self.mode == "recompute_all" or os.environ.get("CODA_B200_SHADOW", "1") == "0":
+            return
+        H, N, C = self.H, self.N, self.C
+        torch.cuda.synchronize(self.dev)
+        torch.cuda.empty_cache()
+        free, _total = torch.cuda.mem_get_info(self.dev)
+        reserve = int(float(os.environ.get("CODA_B200_SHADOW_RESERVE_GB", "6")) * 2 ** 30)
+        per_model = N * C * 4
+        S = int(min(H, max(0, (free - reserve) // per_model)))
+        cap = os.environ.get("CODA_B200_SHADOW_MODELS")
+        if cap is not None:
+            S = min(S, int(cap))
+        if S <= 0:
+            return
+        # disagreement of every model with the ensemble pseudo-label: the models that will need gathers most often
+        dis = torch.zeros(H, dtype=torch.int64, device=self.dev)
+        step = max(1, (64 << 20) // max(1, H))
+        for n0 in range(0, N, step):
+            blk = self.hard[n0:n0 + step].to(torch.int32) & 0xFFFF
+            dis += (blk != self.pseudo[n0:n0 + step, None]).sum(0)
+        order = torch.argsort(dis, descending=True, stable=True)[:S].to(torch.int32)
+        slot = torch.full((H,), -1, dtype=torch.int32, device=self.dev)
+        slot[order.long()] = torch.arange(S, dtype=torch.int32, device=self.dev)
+        self.shadow = self._e((S, C, N), torch.float32)
+        self._call("coda_b200_shadow_build", _ptr(self.preds), H, N, C, _ptr(order), S, _ptr(self.shadow), self._s())
+        self.slot_of_model, self.n_shadow = slot, S
+
     # ------------------------------------------------------------------------ step pieces
     def _tables(self, lo, hi):
         H, C, s = self.H, self.C, self._s()
@@ -232,19 +273,27 @@ class Engine:
             b1 = min(hi, b0 + self.table_batch)
             self._call("coda_b200_beta_tables", _ptr(self.D), _ptr(self.grid), H, C, self.P, self.hyp_w, b0, b1, None,
                        _ptr(self.scratch), _ptr(self.dL), _ptr(self.G0T), _ptr(self.G1T), _ptr(self.PB),
-                       _ptr(self.flags), s, n=3)
+                       _ptr(self.dLb), _ptr(self.Gb), _ptr(self.flags), s, n=3)
 
     def _mixture(self):
         self._call("coda_b200_mixture", _ptr(self.pisum), _ptr(self.PB), self.H, self.C, _ptr(self.pi_hat),
                    _ptr(self.m0), _ptr(self.hb), _ptr(self.best_model), _ptr(self.flags), self._s())
 
     def _pair_rows(self, tile_lo, tile_hi, gains=True, sel=False):
-        cache = _ptr(self.ph_cache)
-        self._call("coda_b200_pair_rows", _ptr(self.tiles), int(tile_lo), int(tile_hi), _ptr(self.zmask),
-                   _ptr(self.dL), _ptr(self.G0T), _ptr(self.G1T), _ptr(self.PB),
-                   _ptr(self.m0) if gains else None, _ptr(self.pi_hat) if gains else None, self.H, cache,
-                   _ptr(self.gain) if gains else None, _ptr(self.sel) if sel else None,
-                   _ptr(self.tile_off) if sel else None, _ptr(self.flags), self._s())
+        tail = (_ptr(self.PB), _ptr(self.m0) if gains else None, _ptr(self.pi_hat) if gains else None, self.H,
+                _ptr(self.ph_cache), _ptr(self.gain) if gains else None, _ptr(self.sel) if sel else None,
+                _ptr(self.tile_off) if sel else None, _ptr(self.flags), self._s())
+        if self.use_tc:
+            self._call("coda_b200_pair_rows_tc", _ptr(self.tiles), int(tile_lo), int(tile_hi), _ptr(self.zmask),
+                       _ptr(self.dLb), _ptr(self.Gb), *tail)
+        else:
+            self._call("coda_b200_pair_rows", _ptr(self.tiles), int(tile_lo), int(tile_hi), _ptr(self.zmask),
+                       _ptr(self.dL), _ptr(self.G0T), _ptr(self.G1T), *tail)
+
+    def _pair_gain(self, filt, cls=None, on_dev=False):
+        self._call("coda_b200_pair_gain", _ptr(self.ph_cache), _ptr(self.pair_cls), self.npairs, self.H,
+                   _ptr(self.PB), _ptr(self.m0), _ptr(self.pi_hat), _ptr(self.gain),
+                   _ptr(self.sel) if on_dev else None, _ptr(self.cls_base), int(cls or 0), filt, self._s())
 
     def post_label(self, idx_global: int | None = None, true_class: int | None = None, device_sel: bool = False):
         """coda.py:316-319: posterior update + marginal refresh + the tables that depend on them.
@@ -268,7 +317,7 @@ class Engine:
             self._tables(0, C)
         else:
             main = torch.cuda.current_stream(self.dev)
-            overlap = self.mode == "incremental" and self.cache_valid
+            overlap = self.overlap and self.mode == "incremental" and self.cache_valid
             if overlap:
                 self.ev_fork.record(main)
                 self.side.wait_event(self.ev_fork)
@@ -279,22 +328,27 @@ class Engine:
                 if device_sel:
                     self._call("coda_b200_beta_tables", _ptr(self.D), _ptr(self.grid), H, C, self.P, self.hyp_w, 0, 1,
                                _ptr(self.sel), _ptr(self.scratch), _ptr(self.dL), _ptr(self.G0T), _ptr(self.G1T),
-                               _ptr(self.PB), _ptr(self.flags), self._s(), n=3)
+                               _ptr(self.PB), _ptr(self.dLb), _ptr(self.Gb), _ptr(self.flags), self._s(), n=3)
                 else:
                     self._tables(true_class, true_class + 1)
-                if overlap:     # refresh the cached rows of the class-t pairs (no gains: m0 / pi_hat not final yet)
+                if self.mode == "incremental" and self.cache_valid:
+                    # refresh the cached rows of the class-t pairs (no gains: m0 / pi_hat are not final yet)
+                    if overlap:
+                        self.ev_tables.record(self.side)
                     if device_sel:
                         self._pair_rows(0, self.max_cls_tiles, gains=False, sel=True)
                     else:
                         self._pair_rows(self.tile_off_host[true_class], self.tile_off_host[true_class + 1], gains=False)
             self.pisum.zero_()
-            self._call("coda_b200_pi_rank1", _ptr(self.preds), _ptr(self.ens), H, N, C, _ptr(self.sel),
-                       _ptr(self.jvec), self.lr, self.fx_shift, _ptr(self.terms), _ptr(self.U), _ptr(self.pisum),
-                       _ptr(self.flags), s, n=4)
+            self._call("coda_b200_pi_rank1", _ptr(self.preds), _ptr(self.ens), _ptr(self.shadow),
+                       _ptr(self.slot_of_model), H, N, C, _ptr(self.sel), _ptr(self.jvec), self.lr, self.fx_shift,
+                       _ptr(self.terms), _ptr(self.U), _ptr(self.pisum), _ptr(self.flags),
+                       4 if overlap else 8, s, n=5)
             self.comm.allreduce_sum_(self.pisum)
             if overlap:
                 self.ev_join.record(self.side)
-                main.wait_event(self.ev_join)
+                main.wait_event(self.ev_tables)     # the mixture needs PB[t]; the rows are awaited in score()
+                self.pending = (None if device_sel else int(true_class), bool(device_sel))
         self._mixture()
         self.scored = False
 
@@ -307,8 +361,14 @@ class Engine:
             if not self.cache_valid:
                 self._pair_rows(0, self.ntiles, gains=False)    # fill the row cache once
                 self.cache_valid = True
-            self._call("coda_b200_pair_gain", _ptr(self.ph_cache), _ptr(self.pair_cls), self.npairs, self.H,
-                       _ptr(self.PB), _ptr(self.m0), _ptr(self.pi_hat), _ptr(self.gain), s)
+            if self.pending is None:
+                self._pair_gain(0)
+            else:   # gains of every other class while the side stream still rebuilds the class-t rows
+                cls, on_dev = self.pending
+                self._pair_gain(1, cls, on_dev)
+                torch.cuda.current_stream(self.dev).wait_event(self.ev_join)
+                self._pair_gain(2, cls, on_dev)
+                self.pending = None
         else:
             self._pair_rows(0, self.ntiles)
         self._call("coda_b200_eig_points", _ptr(self.U), N, C, _ptr(self.ent_off), _ptr(self.ent_pair),

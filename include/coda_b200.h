@@ -85,13 +85,20 @@ int coda_b200_label_row(const uint16_t* hard, int H, int64_t N, const int64_t* s
 /* D[h][t][jvec[h]] += lr  (coda.py:317). */
 int coda_b200_label_apply(float* D, int H, int C, const int64_t* sel, const int32_t* jvec, double lr,
                           coda_stream_t stream);
+/* Optional class-major shadow copy T[s][c][n] = preds[model_of_slot[s]][n][c] for S of the H models (no
+ * reference counterpart: a layout for the one-float-per-(model, item) gather of the rank-1 refresh). */
+int coda_b200_shadow_build(const float* preds, int H, int64_t N, int C, const int32_t* model_of_slot, int S, float* T,
+                           coda_stream_t stream);
 /* update_pi_hat after the rank-1 change of D (coda.py:319): U[n][t] += lr * sum_h preds[h][n][jvec[h]],
  * then the same normalise + column sums as pi_reduce.  With ens != NULL (scan_slab's ens_out) the sum over
  * models is taken as E[n][t'] + corrections for the models that disagree with the majority class t' of
- * jvec (exact algebra, fewer gathers).  terms: int32 scratch [2 + 6*H]. */
-int coda_b200_pi_rank1(const float* preds, const float* ens, int H, int64_t N, int C, const int64_t* sel,
-                       const int32_t* jvec, double lr, int fx_shift, int32_t* terms, float* U, int64_t* pisum_fx,
-                       uint32_t* flags, coda_stream_t stream);
+ * jvec (exact algebra, fewer gathers).  shadow/slot_of_model (optional): models with slot_of_model[h] >= 0
+ * are read from the shadow copy.  terms: int32 scratch [2 + 8*H], 8-byte aligned.  ctas_per_sm (1..8)
+ * bounds the grid so a concurrent stream keeps SM resources. */
+int coda_b200_pi_rank1(const float* preds, const float* ens, const float* shadow, const int32_t* slot_of_model, int H,
+                       int64_t N, int C, const int64_t* sel, const int32_t* jvec, double lr, int fx_shift,
+                       int32_t* terms, float* U, int64_t* pisum_fx, uint32_t* flags, int ctas_per_sm,
+                       coda_stream_t stream);
 /* cudaLimitMaxL2FetchGranularity hint (32/64/128 B) for the sector-gather kernels. */
 int coda_b200_set_l2_fetch_granularity(int bytes);
 
@@ -99,10 +106,12 @@ int coda_b200_set_l2_fetch_granularity(int bytes);
  *      coda.py:77-119, batch_update_beta coda.py:150-168) for classes [cls_lo, cls_hi) ------- */
 size_t coda_b200_tables_scratch_bytes(int H, int ncls);
 /* sel (optional, device): {idx, class}; when non-NULL exactly one class, sel[1], is rebuilt (host-free loop). */
+/* dLb / Gb (optional, both or neither): the same tables as bf16 limbs in tensor-core operand order for
+ * coda_b200_pair_rows_tc: dLb [C][Hp/32][3][256*32], Gb [C][16][4][Hp*16] bf16, zero-initialised by the caller. */
 int coda_b200_beta_tables(const float* D, const float* grid_x, int H, int C, int P, double hyp_w, int cls_lo,
                           int cls_hi, const int64_t* sel, void* scratch, float* dL /*[C][H][P]*/,
-                          float* G0T /*[C][P][Hp]*/, float* G1T /*[C][P][Hp]*/, float* PB /*[C][Hp]*/,
-                          uint32_t* flags, coda_stream_t stream);
+                          float* G0T /*[C][P][Hp]*/, float* G1T /*[C][P][Hp]*/, float* PB /*[C][Hp]*/, void* dLb,
+                          void* Gb, uint32_t* flags, coda_stream_t stream);
 
 /* pi_hat (coda.py:232-233), P(best) vector m0 == get_pbest() (coda.py:253, 325-332), H_before
  * (coda.py:254) and argmax (coda.py:346). */
@@ -124,9 +133,18 @@ int coda_b200_pair_rows(const int32_t* tiles, int tile_lo, int tile_hi, const ui
                         const float* G0T, const float* G1T, const float* PB, const float* m0, const float* pi_hat,
                         int H, float* ph_cache, float* gain, const int64_t* sel /*optional*/,
                         const int64_t* tile_off /*[C+1], with sel*/, uint32_t* flags, coda_stream_t stream);
-/* gain for every pair from cached rows (coda.py:274-276 only). */
+/* The same computation on the tcgen05 tensor cores (Hp <= 256): tiles128 are tiles of <= 128 same-class pairs,
+ * operands come from the bf16 limb tables of coda_b200_beta_tables. */
+int coda_b200_pair_rows_tc(const int32_t* tiles128, int tile_lo, int tile_hi, const uint32_t* zmask, const void* dLb,
+                           const void* Gb, const float* PB, const float* m0, const float* pi_hat, int H,
+                           float* ph_cache, float* gain, const int64_t* sel, const int64_t* tile_off, uint32_t* flags,
+                           coda_stream_t stream);
+/* gain for every pair from cached rows (coda.py:274-276 only).  filter: 0 = all pairs, 1 = all but class t,
+ * 2 = only class t, with t = sel[1] when sel != NULL (device) else cls_host; cls_base [C+1] gives the pair-id
+ * range of every class.  (1 then 2 lets the class-t row refresh overlap the rest of the stream.) */
 int coda_b200_pair_gain(const float* ph_cache, const uint16_t* pair_cls, int64_t npairs, int H, const float* PB,
-                        const float* m0, const float* pi_hat, float* gain, coda_stream_t stream);
+                        const float* m0, const float* pi_hat, float* gain, const int64_t* sel,
+                        const int64_t* cls_base, int cls_host, int filter, coda_stream_t stream);
 
 /* ---- selection (coda.py:278, get_next_item_to_label coda.py:283-313) -------------------- */
 int coda_b200_eig_blocks(int64_t N); /* number of partial records eig_points writes */

@@ -315,3 +315,27 @@ def test_prefilter_n_subsample_path():
     sel = _mk(preds, labels, prefilter_n=50)
     i, q = sel.get_next_item_to_label()
     assert i == i_ref and abs(q - q_ref) < EIG_ATOL and random.getstate() == state_ref and sel.stochastic
+
+
+def test_tensor_core_rows_match_simt_rows(monkeypatch):
+    """pairs_tc.cu (tcgen05, bf16 limbs) against pairs.cu (fp32 SIMT) on the same tables: per-item EIG and P(best)."""
+    from coda_b200.synth import synth
+    for (H, N, C, seed) in [(256, 6000, 20, 3), (40, 3000, 12, 2), (100, 2000, 7, 6)]:
+        preds, labels = synth(H, N, C, seed=seed)
+        out = {}
+        for tc in ("1", "0"):
+            monkeypatch.setenv("CODA_B200_TC", tc)
+            random.seed(0)
+            s = _mk(preds, labels, mode="incremental")
+            assert s.engine.use_tc == (tc == "1")
+            eigs = []
+            for k in range(3):
+                idx, q = s.get_next_item_to_label()
+                eigs.append(s.engine.eig.cpu().numpy().copy())
+                if k == 0:
+                    first = idx
+                s.add_label(first + k, int(labels[first + k]), q)      # same labels on both paths
+                s.get_best_model_prediction()
+            out[tc] = (np.stack(eigs), s.get_pbest().cpu().numpy())
+        np.testing.assert_allclose(out["1"][0], out["0"][0], atol=2e-7, rtol=0)
+        np.testing.assert_allclose(out["1"][1], out["0"][1], atol=1e-7, rtol=0)

@@ -192,6 +192,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
         comm = TorchComm()
     else:
@@ -284,7 +286,8 @@ def main():
     sel, t_init = make(args.mode)
     eng = sel.engine
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    hot = ["coda_b200_pi_rank1", "coda_b200_pair_gain", "coda_b200_pair_rows", "coda_b200_eig_points", "coda_b200_pi_full"]
+    hot = ["coda_b200_pi_rank1", "coda_b200_pair_gain", "coda_b200_pair_rows", "coda_b200_pair_rows_tc",
+           "coda_b200_eig_points", "coda_b200_pi_full"]
     ms, launches, prof, picks_dev = device_loop(sel, args.warmup, args.steps, profile_only=hot)
     clocks = sampler.stop() if sampler else {}
     value = args.steps / (ms / 1e3)
@@ -328,10 +331,18 @@ def main():
                     "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
                     "avg_launch_ms": avg_ms, "algorithmic_bytes_per_launch": alg_bytes[dom],
                     "share_of_step": tot / ms}
-        else:   # pair_rows: fp32 FMA bound (not HBM): report against the FP32 pipe
-            cells = 3 * 32 * 256 * eng.Hp     # FMA per pair-slot per tile row: phase A + two tables
-            roof = {"kernel": dom.replace("coda_b200_", "k_"), "bound": "fp32", "avg_launch_ms": avg_ms,
-                    "share_of_step": tot / ms, "achieved": None, "peak": None, "unit": "TFLOP/s", "frac": None,
+        elif dom == "coda_b200_pair_rows_tc":
+            # 9 bf16 MMAs of 128 x 256 x Hp (3 dL limbs) / 128 x Hp x 256 (2 tables x 3 cross terms) per 128-pair tile
+            tiles_per_launch = eng.ntiles if args.mode != "incremental" else max(1, eng.ntiles // C)
+            flops = 9 * 2 * 128 * 256 * eng.Hp * tiles_per_launch
+            tf_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+            ach = flops / (avg_ms * 1e-3) / 1e12
+            roof = {"kernel": "k_pair_rows_tc", "bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s",
+                    "frac": ach / tf_peak, "traffic": None, "peak_source": peak_src, "avg_launch_ms": avg_ms,
+                    "algorithmic_flops_per_launch": flops, "share_of_step": tot / ms}
+        else:
+            roof = {"kernel": dom.replace("coda_b200_", "k_"), "bound": "hbm", "avg_launch_ms": avg_ms,
+                    "share_of_step": tot / ms, "achieved": None, "peak": hbm_peak, "unit": "GB/s", "frac": None,
                     "traffic": None}
 
     cpu = None
@@ -348,7 +359,7 @@ def main():
                 "workload": f"synthetic M={H} N={N} C={C} ({args.workload}{', dense' if args.dense else ''}), N-axis sharded over {world} GPU(s)",
                 "mode": args.mode, "l2": "per-step working set (slab gather + row cache + U) >> 126 MB L2; no flush needed",
                 "tie_rule_value": "lowest index (device loop)", "tie_rule_e2e": "random.choice (coda.py:308)",
-                "pairs": npairs, "heavy_pairs": eng.n_heavy, "entries_per_item": eng.n_entries / max(1, n_loc),
+                "pairs": npairs, "heavy_pairs": eng.n_heavy, "tensor_core_rows": bool(eng.use_tc), "entries_per_item": eng.n_entries / max(1, n_loc),
                 "gen_s": t_gen, "init_s": t_init, "shadow_models": eng.n_shadow,
             },
             "clocks": clocks,

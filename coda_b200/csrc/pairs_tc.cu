@@ -24,7 +24,8 @@ constexpr int TC_M = 128;        // pairs per tile
 constexpr int TC_NODES = 256;    // quadrature nodes
 constexpr int KA = 32;           // models per phase-A chunk
 constexpr int KB = 16;           // nodes per phase-B chunk
-constexpr int STAGES_A = 2;
+constexpr int STAGES_A = 3;
+constexpr int TC_THREADS = 256;   // warps 0-3: columns [0, half), warps 4-7: columns [half, end) of their TMEM lane quadrant
 constexpr int STAGES_B = 3;
 
 struct TcArgs {
@@ -102,10 +103,12 @@ __device__ __forceinline__ uint32_t core_off(int r, int k, int rows) {
   return (uint32_t)(((k >> 3) * (rows >> 3) + (r >> 3)) * 128 + (r & 7) * 16 + (k & 7) * 2);
 }
 
-__global__ void __launch_bounds__(TC_M, 1) k_pair_rows_tc(TcArgs a, int tile0) {
+__global__ void __launch_bounds__(TC_THREADS, 1) k_pair_rows_tc(TcArgs a, int tile0) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int H = a.H, Hp = a.Hp, W = a.W;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int quad = warp & 3, half = warp >> 2;      // TMEM lane quadrant (hardware: warp % 4), column half
+  const int row = quad * 32 + lane;                 // this thread's pair within the tile
   if (a.sel) {
     const long long t = a.sel[1];
     tile0 = (int)a.tile_off[t];
@@ -115,8 +118,10 @@ __global__ void __launch_bounds__(TC_M, 1) k_pair_rows_tc(TcArgs a, int tile0) {
   const int c = tile.x, pid0 = tile.y, cnt = tile.z;
 
   // ---- shared memory carve-up ----------------------------------------------------------------
-  // [0, 128K)          phase A: Z operand (first 64K max) | phase B: D hi (64K) + D lo (64K)
-  // [128K, 128K+96K)   phase A: 2 stages x 48K (3 limbs x 256 x KA bf16) | phase B: 3 stages x 32K (4 tables x Hp x KB)
+  // [0, 64K)           phase A: Z operand                       | phase B: D hi
+  // [64K, 208K)        phase A: 3 stages x 48K (3 limbs x 256 x KA bf16)
+  // [64K, 128K)                                                 | phase B: D lo
+  // [128K, 224K)                                                | phase B: 3 stages x 32K (4 tables x Hp x KB)
   // tail               barriers, TMEM base, m0 / PB rows
   unsigned char* opA = smem;
   unsigned char* stg = smem + 128 * 1024;
@@ -130,6 +135,9 @@ __global__ void __launch_bounds__(TC_M, 1) k_pair_rows_tc(TcArgs a, int tile0) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(doneB + 1);
   float* m0s = reinterpret_cast<float*>(tmem_slot + 2);       // [Hp]
   float* pbs = m0s + Hp;                                      // [Hp]
+  float* xsum = reinterpret_cast<float*>(stg);                // [2][128] row-sum halves  (stage region: idle in epilogue B)
+  float* xgain = xsum + 2 * TC_M;                             // [2][128] gain halves
+  unsigned char* stgA = smem + 64 * 1024;
 
   if (tid == 0) {
     for (int i = 0; i < STAGES_A; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
@@ -145,17 +153,17 @@ __global__ void __launch_bounds__(TC_M, 1) k_pair_rows_tc(TcArgs a, int tile0) {
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   const bool want_gain = a.gain != nullptr;
-  for (int h = tid; h < Hp; h += TC_M) {
+  for (int h = tid; h < Hp; h += TC_THREADS) {
     m0s[h] = (want_gain && h < H) ? a.m0[h] : 0.f;
     pbs[h] = a.PB[(size_t)c * Hp + h];
   }
   // ---- Z operand: row = this thread's pair, K = models, bf16 {0, 1} ----------------------------
   uint32_t zw[8];
 #pragma unroll
-  for (int w = 0; w < 8; ++w) zw[w] = (w < W && tid < cnt) ? a.zmask[(size_t)(pid0 + tid) * W + w] : 0u;
+  for (int w = 0; w < 8; ++w) zw[w] = (w < W && row < cnt) ? a.zmask[(size_t)(pid0 + row) * W + w] : 0u;
 #pragma unroll
   for (int w = 0; w < 8; ++w) {
-    if (w < W) {
+    if (w < W && (w & 1) == half) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {   // 8 models -> one 16-byte core row
         const uint32_t b = zw[w] >> (8 * q);
@@ -164,7 +172,7 @@ __global__ void __launch_bounds__(TC_M, 1) k_pair_rows_tc(TcArgs a, int tile0) {
         v.y = ((b & 4u) ? 0x3F80u : 0u) | ((b & 8u) ? 0x3F800000u : 0u);
         v.z = ((b & 16u) ? 0x3F80u : 0u) | ((b & 32u) ? 0x3F800000u : 0u);
         v.w = ((b & 64u) ? 0x3F80u : 0u) | ((b & 128u) ? 0x3F800000u : 0u);
-        *reinterpret_cast<uint4*>(opA + core_off(tid, w * 32 + q * 8, TC_M)) = v;
+        *reinterpret_cast<uint4*>(opA + core_off(row, w * 32 + q * 8, TC_M)) = v;
       }
     }
   }
@@ -173,7 +181,7 @@ __global__ void __launch_bounds__(TC_M, 1) k_pair_rows_tc(TcArgs a, int tile0) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t opA_s = smem_u32(opA), stg_s = smem_u32(stg);
+  const uint32_t opA_s = smem_u32(opA), stg_s = smem_u32(stg), stgA_s = smem_u32(stgA);
   const int nka = Hp / KA;                       // phase-A chunks
   constexpr int nkb = TC_NODES / KB;             // phase-B chunks
   const uint32_t bytesA = 3u * TC_NODES * KA * 2u;          // per stage
@@ -184,15 +192,18 @@ __global__ void __launch_bounds__(TC_M, 1) k_pair_rows_tc(TcArgs a, int tile0) {
   if (tid == 0) {
     const unsigned char* src = reinterpret_cast<const unsigned char*>(a.dLb) + (size_t)c * nka * bytesA;
     const uint32_t idesc = instr_desc_bf16(TC_NODES);
-    mbar_expect_tx(&fullA[0], bytesA);
-    tma_load_1d(stg, src, bytesA, &fullA[0]);
+    for (int kc = 0; kc < STAGES_A - 1 && kc < nka; ++kc) {
+      mbar_expect_tx(&fullA[kc], bytesA);
+      tma_load_1d(stgA + (size_t)kc * 48 * 1024, src + (size_t)kc * bytesA, bytesA, &fullA[kc]);
+    }
     for (int kc = 0; kc < nka; ++kc) {
       const int s = kc % STAGES_A;
-      if (kc + 1 < nka) {
-        const int s1 = (kc + 1) % STAGES_A;
-        if (kc + 1 >= STAGES_A) mbar_wait_bounded(&emptyA[s1], (((kc + 1) / STAGES_A) - 1) & 1);
+      const int kn = kc + STAGES_A - 1;
+      if (kn < nka) {
+        const int s1 = kn % STAGES_A;
+        if (kn >= STAGES_A) mbar_wait_bounded(&emptyA[s1], ((kn / STAGES_A) - 1) & 1);
         mbar_expect_tx(&fullA[s1], bytesA);
-        tma_load_1d(stg + (size_t)s1 * 48 * 1024, src + (size_t)(kc + 1) * bytesA, bytesA, &fullA[s1]);
+        tma_load_1d(stgA + (size_t)s1 * 48 * 1024, src + (size_t)kn * bytesA, bytesA, &fullA[s1]);
       }
       mbar_wait_bounded(&fullA[s], (kc / STAGES_A) & 1);
       tc_fence_after();
@@ -203,7 +214,7 @@ __global__ void __launch_bounds__(TC_M, 1) k_pair_rows_tc(TcArgs a, int tile0) {
           // A: Z tile [k_core][16 r_core]: LBO = 16 * 128, advance 2 k-cores per K=16 step
           const uint64_t ad = smem_desc(opA_s + (uint32_t)(kc * (KA / 8) + ks * 2) * (TC_M / 8) * 128, (TC_M / 8) * 128, 128);
           // B: limb tile [4 k_core][32 r_core]: LBO = 32 * 128
-          const uint64_t bd = smem_desc(stg_s + (uint32_t)s * 48 * 1024 + (uint32_t)limb * (TC_NODES * KA * 2) +
+          const uint64_t bd = smem_desc(stgA_s + (uint32_t)s * 48 * 1024 + (uint32_t)limb * (TC_NODES * KA * 2) +
                                             (uint32_t)(ks * 2) * (TC_NODES / 8) * 128,
                                         (TC_NODES / 8) * 128, 128);
           mma_bf16(tmem, ad, bd, idesc, (kc | limb | ks) ? 1u : 0u);
@@ -229,9 +240,9 @@ __global__ void __launch_bounds__(TC_M, 1) k_pair_rows_tc(TcArgs a, int tile0) {
   {
     unsigned char* dhi = opA;
     unsigned char* dlo = opA + 64 * 1024;
-    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t trow = tmem + ((uint32_t)(quad * 32) << 16);
 #pragma unroll 1
-    for (int cc = 0; cc < TC_NODES / 32; ++cc) {
+    for (int cc = half * (TC_NODES / 64); cc < (half + 1) * (TC_NODES / 64); ++cc) {
       float v[32];
       tmem_ld32(trow + cc * 32, v);
 #pragma unroll
@@ -244,7 +255,7 @@ __global__ void __launch_bounds__(TC_M, 1) k_pair_rows_tc(TcArgs a, int tile0) {
           hi[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
           lo[e] = pack_bf16(d0 - __bfloat162float(h0), d1 - __bfloat162float(h1));
         }
-        const uint32_t off = core_off(tid, cc * 32 + g * 8, TC_M);
+        const uint32_t off = core_off(row, cc * 32 + g * 8, TC_M);
         *reinterpret_cast<uint4*>(dhi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
         *reinterpret_cast<uint4*>(dlo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
       }
@@ -291,14 +302,15 @@ __global__ void __launch_bounds__(TC_M, 1) k_pair_rows_tc(TcArgs a, int tile0) {
   mbar_wait_bounded(doneB, 0);
   tc_fence_after();
 
-  // ---- epilogue B: thread <-> pair ----------------------------------------------------------------
+  // ---- epilogue B: (pair, column half) per thread ---------------------------------------------------
   {
-    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t trow = tmem + ((uint32_t)(quad * 32) << 16);
     const int nch = Hp / 32;
+    const int ch_lo = half ? (nch + 1) / 2 : 0, ch_hi = half ? nch : (nch + 1) / 2;
     float sum = 0.f;
 #pragma unroll
     for (int ch = 0; ch < 8; ++ch) {
-      if (ch < nch) {
+      if (ch >= ch_lo && ch < ch_hi) {
         float p0[32], p1[32];
         tmem_ld32(trow + ch * 32, p0);
         tmem_ld32(trow + 256 + ch * 32, p1);
@@ -307,15 +319,18 @@ __global__ void __launch_bounds__(TC_M, 1) k_pair_rows_tc(TcArgs a, int tile0) {
         for (int i = 0; i < 32; ++i) sum += ((zb >> i) & 1u) ? p1[i] : p0[i];
       }
     }
+    xsum[half * TC_M + row] = sum;
+    __syncthreads();
+    sum = xsum[row] + xsum[TC_M + row];
     uint32_t bad = 0;
-    if (tid < cnt && !isfinite(sum)) bad = CODA_B200_FLAG_NONFINITE_EIG;
-    const float den = fmaxf(sum, 1e-30f);                            // coda.py:114
+    if (row < cnt && half == 0 && !isfinite(sum)) bad = CODA_B200_FLAG_NONFINITE_EIG;
+    const float rden = 1.0f / fmaxf(sum, 1e-30f);                    // coda.py:114
     const float pic = want_gain ? a.pi_hat[c] : 0.f;
     float g = 0.f;
-    float* cache = (a.ph_cache && tid < cnt) ? a.ph_cache + (size_t)(pid0 + tid) * Hp : nullptr;
+    float* cache = (a.ph_cache && row < cnt) ? a.ph_cache + (size_t)(pid0 + row) * Hp : nullptr;
 #pragma unroll
     for (int ch = 0; ch < 8; ++ch) {
-      if (ch >= nch) continue;
+      if (ch < ch_lo || ch >= ch_hi) continue;
       float p0[32], p1[32];
       tmem_ld32(trow + ch * 32, p0);
       tmem_ld32(trow + 256 + ch * 32, p1);
@@ -323,7 +338,7 @@ __global__ void __launch_bounds__(TC_M, 1) k_pair_rows_tc(TcArgs a, int tile0) {
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         const int h = ch * 32 + i;
-        float ph = (((zb >> i) & 1u) ? p1[i] : p0[i]) / den;
+        float ph = (((zb >> i) & 1u) ? p1[i] : p0[i]) * rden;
         if (h >= H) ph = 0.f;
         p0[i] = ph;
         if (want_gain && h < H) {
@@ -337,7 +352,11 @@ __global__ void __launch_bounds__(TC_M, 1) k_pair_rows_tc(TcArgs a, int tile0) {
           *reinterpret_cast<float4*>(cache + ch * 32 + i) = make_float4(p0[i], p0[i + 1], p0[i + 2], p0[i + 3]);
       }
     }
-    if (want_gain && tid < cnt) a.gain[pid0 + tid] = g;
+    if (want_gain) {
+      xgain[half * TC_M + row] = g;
+      __syncthreads();
+      if (half == 0 && row < cnt) a.gain[pid0 + row] = xgain[row] + xgain[TC_M + row];
+    }
     if (bad) atomicOr(a.flags, bad);
   }
   tc_fence_before();
@@ -370,7 +389,7 @@ extern "C" int coda_b200_pair_rows_tc(const int32_t* tiles128, int tile_lo, int 
   a.H = H; a.Hp = Hp; a.W = Hp / 32;
   const size_t smem = (size_t)(128 + 96) * 1024 + 256 + (size_t)2 * Hp * 4;
   CODA_CUDA_OK(cudaFuncSetAttribute(k_pair_rows_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_pair_rows_tc<<<tile_hi - tile_lo, TC_M, smem, as_stream(stream)>>>(a, tile_lo);
+  k_pair_rows_tc<<<tile_hi - tile_lo, TC_THREADS, smem, as_stream(stream)>>>(a, tile_lo);
   CODA_LAUNCH_OK("k_pair_rows_tc");
   return CODA_B200_OK;
 }

@@ -35,6 +35,7 @@ SIGNATURES = {
     "coda_b200_device_check": (i32, []),
     "coda_b200_scan_slab": (i32, [p, i32, i64, i32, p, p, p, p, p, p]),
     "coda_b200_confusion_accum": (i32, [p, p, i32, i64, i32, i32, p, p]),
+    "coda_b200_confusion_sorted": (i32, [p, p, p, i32, i64, i32, i32, p, p]),
     "coda_b200_init_dirichlets": (i32, [p, i32, i32, i32, f64, f64, i32, p, p]),
     "coda_b200_pi_full": (i32, [p, p, i32, i64, i32, p, p]),
     "coda_b200_pi_reduce": (i32, [p, i64, i32, i32, p, p, p, p]),
@@ -52,7 +53,8 @@ SIGNATURES = {
     "coda_b200_pair_rows": (i32, [p, i32, i32, p, p, p, p, p, p, p, i32, p, p, p, p, p, p]),
     "coda_b200_pair_gain": (i32, [p, p, i64, i32, p, p, p, p, p, p, i32, i32, p]),
     "coda_b200_eig_blocks": (i32, [i64]),
-    "coda_b200_eig_points": (i32, [p, i64, i32, p, p, p, p, p, p, p, i64, p, p, p, p]),
+    "coda_b200_eig_points": (i32, [p, i64, i32, p, p, p, p, p, p, p, i64, p, i32, p, p, p, p]),
+    "coda_b200_ell_build": (i32, [p, p, p, i64, i32, p, p]),
     "coda_b200_select_merge": (i32, [p, i32, p, p]),
     "coda_b200_ties": (i32, [p, i64, p, p, i64, p, i32, p, p, p, p]),
     "coda_b200_device_pick": (i32, [p, p, i64, i64, p, p, p, p, i64, p]),

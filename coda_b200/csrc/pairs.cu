@@ -492,6 +492,9 @@ __global__ void __launch_bounds__(256) k_pair_gain_fast(const float* __restrict_
     if (p0 >= skip_lo && p1 <= skip_hi) continue;          // chunk entirely inside the excluded class
     for (long long i = p0; i < p1; i += 4) {
       float4 a[4][NQ];
+      int cls4[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) cls4[j] = pair_cls[min(i + j, npairs - 1)];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const long long pid = min(i + j, npairs - 1);
@@ -503,7 +506,7 @@ __global__ void __launch_bounds__(256) k_pair_gain_fast(const float* __restrict_
       for (int j = 0; j < 4; ++j) {
         const long long pid = i + j;
         if (pid < p1 && !(pid >= skip_lo && pid < skip_hi)) {
-          const int c = pair_cls[pid];
+          const int c = cls4[j];
           if (c != cur) {
             cur = c;
             pic = pi_hat[c];

@@ -38,6 +38,7 @@ __global__ void __launch_bounds__(256) k_eig_points(const float* __restrict__ U,
                                                     const long long* __restrict__ cls_base,
                                                     const uint8_t* __restrict__ labeled,
                                                     const uint8_t* __restrict__ disagree, long long n_offset,
+                                                    const int2* __restrict__ ell, int ellK,
                                                     float* __restrict__ eig, long long* __restrict__ partials,
                                                     uint32_t* __restrict__ flags) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -69,14 +70,30 @@ __global__ void __launch_bounds__(256) k_eig_points(const float* __restrict__ U,
           u[i][k] = c < C ? __ldg(U + (size_t)n * C + c) : 0.f;
         }
       }
-      o0[i] = __ldg(ent_off + n);
-      o1[i] = __ldg(ent_off + n + 1);
+      if (!ell) {
+        o0[i] = __ldg(ent_off + n);
+        o1[i] = __ldg(ent_off + n + 1);
+      } else {
+        o0[i] = 0; o1[i] = 0;
+      }
     }
     int ec[IT], ep[IT];
+    if (ell) {
+      // ELL copy of the CSR lists ([N][ellK] x {pair id, class}, -1 padded, ellK >= longest list): the entry
+      // address follows from the item index, so these loads are issued together with the U rows above
 #pragma unroll
-    for (int i = 0; i < IT; ++i) {
-      ec[i] = -1; ep[i] = 0;
-      if (o0[i] + lane < o1[i]) { ec[i] = ent_cls[o0[i] + lane]; ep[i] = ent_pair[o0[i] + lane]; }
+      for (int i = 0; i < IT; ++i) {
+        const long long n = min(nb + i, N - 1);
+        int2 e2 = make_int2(0, -1);
+        if (lane < ellK) e2 = __ldg(ell + (size_t)n * ellK + lane);
+        ep[i] = e2.x; ec[i] = e2.y;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < IT; ++i) {
+        ec[i] = -1; ep[i] = 0;
+        if (o0[i] + lane < o1[i]) { ec[i] = ent_cls[o0[i] + lane]; ep[i] = ent_pair[o0[i] + lane]; }
+      }
     }
     float eg[IT], eu[IT];
 #pragma unroll
@@ -154,18 +171,20 @@ extern "C" int coda_b200_eig_blocks(int64_t N) {
 
 extern "C" int coda_b200_eig_points(const float* U, int64_t N, int C, const int64_t* ent_off, const int32_t* ent_pair,
                                     const uint16_t* ent_cls, const float* gain, const int64_t* cls_base,
-                                    const uint8_t* labeled, const uint8_t* disagree, int64_t n_offset, float* eig,
-                                    int64_t* partials, uint32_t* flags, coda_stream_t stream) {
+                                    const uint8_t* labeled, const uint8_t* disagree, int64_t n_offset,
+                                    const int32_t* ell, int ell_k, float* eig, int64_t* partials, uint32_t* flags,
+                                    coda_stream_t stream) {
   CODA_CHECK_ARG(U && ent_off && ent_pair && ent_cls && gain && cls_base && labeled && disagree && eig && partials && flags,
                  "eig_points: null pointer");
   size_t smem = (size_t)C * 4;
   CODA_CHECK_ARG(smem <= 48 * 1024, "eig_points: C=%d too large", C);
+  CODA_CHECK_ARG(!ell || (ell_k >= 1 && ell_k <= 32), "eig_points: ell_k=%d out of range", ell_k);
   int grid = coda_b200_eig_blocks(N);
 #define LAUNCH_EP(KC)                                                                                              \
   k_eig_points<KC><<<grid, 256, smem, as_stream(stream)>>>(                                                        \
       U, N, C, reinterpret_cast<const long long*>(ent_off), ent_pair, ent_cls, gain,                               \
-      reinterpret_cast<const long long*>(cls_base), labeled, disagree, n_offset, eig,                              \
-      reinterpret_cast<long long*>(partials), flags)
+      reinterpret_cast<const long long*>(cls_base), labeled, disagree, n_offset,                                   \
+      reinterpret_cast<const int2*>(ell), ell_k, eig, reinterpret_cast<long long*>(partials), flags)
   if (C <= 32) LAUNCH_EP(1);
   else if (C <= 64) LAUNCH_EP(2);
   else if (C <= 128) LAUNCH_EP(4);
@@ -290,5 +309,26 @@ extern "C" int coda_b200_device_pick(const int64_t* tie_hdr, const int64_t* labe
                                                 reinterpret_cast<long long*>(sel),
                                                 reinterpret_cast<long long*>(hist_idx), hist_q, step);
   CODA_LAUNCH_OK("k_device_pick");
+  return CODA_B200_OK;
+}
+
+// ELL copy of the per-item CSR lists (eig_points): ell[n][k] = {pair id, class}, {0, -1} padding.
+__global__ void k_ell_build(const long long* __restrict__ ent_off, const int32_t* __restrict__ ent_pair,
+                            const uint16_t* __restrict__ ent_cls, long long N, int K, int2* __restrict__ ell) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * K) return;
+  const long long n = i / K;
+  const int k = (int)(i % K);
+  const long long o = ent_off[n] + k;
+  ell[i] = o < ent_off[n + 1] ? make_int2(ent_pair[o], (int)ent_cls[o]) : make_int2(0, -1);
+}
+
+extern "C" int coda_b200_ell_build(const int64_t* ent_off, const int32_t* ent_pair, const uint16_t* ent_cls, int64_t N,
+                                   int K, int32_t* ell, coda_stream_t stream) {
+  CODA_CHECK_ARG(ent_off && ent_pair && ent_cls && ell && K >= 1 && K <= 32, "ell_build: bad arguments");
+  const long long tot = (long long)N * K;
+  k_ell_build<<<(unsigned)((tot + 255) / 256), 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const long long*>(ent_off), ent_pair, ent_cls, N, K, reinterpret_cast<int2*>(ell));
+  CODA_LAUNCH_OK("k_ell_build");
   return CODA_B200_OK;
 }

@@ -78,10 +78,151 @@ __global__ void __launch_bounds__(256) k_scan_slab(const float* __restrict__ pre
   if (bad) atomicOr(flags, bad);
 }
 
+// Fast path (C <= 128, N*C % 4 == 0): the [TN x C] tile of every model is one contiguous blob, staged into
+// shared memory by 1-D bulk TMA (cp.async.bulk + mbarrier) through a SS_ST-deep ring, so HBM reads run ahead
+// of the arg-max / ensemble arithmetic.  Each warp owns 4 rows of the tile (ILP over the four shuffle chains);
+// the ensemble sums live in registers.
+#define SS_TN 32
+#define SS_ST 4
+template <int KC>
+__global__ void __launch_bounds__(256) k_scan_slab_tma(const float* __restrict__ preds, int H, long long N, int C,
+                                                       uint16_t* __restrict__ hard, int32_t* __restrict__ pseudo,
+                                                       uint8_t* __restrict__ disagree, float* __restrict__ ens_out,
+                                                       uint32_t* __restrict__ flags) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tile_floats = SS_TN * C;
+  const size_t buf_bytes = ((size_t)tile_floats * 4 + 127) / 128 * 128;
+  float* bufs = reinterpret_cast<float*>(smem_raw);                                    // [SS_ST][tile]
+  uint16_t* hard_t = reinterpret_cast<uint16_t*>(smem_raw + SS_ST * buf_bytes);         // [SS_TN][H]
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + SS_ST * buf_bytes + (((size_t)SS_TN * H * 2 + 15) / 16) * 16);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long n0 = (long long)blockIdx.x * SS_TN;
+  const int tn = (int)min((long long)SS_TN, N - n0);
+  const uint32_t bytes = (uint32_t)tn * C * 4;          // multiple of 16: callers guarantee (tn * C) % 4 == 0
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < SS_ST; ++s) mbar_init(&full[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < SS_ST && s < H; ++s) {
+      mbar_expect_tx(&full[s], bytes);
+      tma_load_1d(reinterpret_cast<unsigned char*>(bufs) + s * buf_bytes, preds + ((size_t)s * N + n0) * C, bytes, &full[s]);
+    }
+  }
+  float ens[4][KC];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int k = 0; k < KC; ++k) ens[r][k] = 0.f;
+  uint32_t bad = 0;
+  for (int h = 0; h < H; ++h) {
+    const int s = h % SS_ST;
+    mbar_wait(&full[s], (h / SS_ST) & 1);
+    const float* buf = reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(bufs) + s * buf_bytes);
+    float bv[4];
+    int bi[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int p = warp + 8 * r;
+      bv[r] = -INFINITY;
+      bi[r] = 0x7fffffff;
+      if (p < tn) {
+#pragma unroll
+        for (int k = 0; k < KC; ++k) {
+          const int c = lane + 32 * k;
+          if (c < C) {
+            const float v = buf[p * C + c];
+            if (!isfinite(v)) bad |= CODA_B200_FLAG_NONFINITE_INPUT;
+            if (v < 0.f || v > 1.0001f) bad |= CODA_B200_FLAG_RANGE_INPUT;
+            ens[r][k] += v;
+            if (v > bv[r]) { bv[r] = v; bi[r] = c; }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const float ov = __shfl_xor_sync(CODA_FULL, bv[r], o);
+        const int oi = __shfl_xor_sync(CODA_FULL, bi[r], o);
+        if (ov > bv[r] || (ov == bv[r] && oi < bi[r])) { bv[r] = ov; bi[r] = oi; }
+      }
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int p = warp + 8 * r;
+        if (p < tn) hard_t[(size_t)p * H + h] = (uint16_t)(bi[r] == 0x7fffffff ? 0 : bi[r]);
+      }
+    }
+    __syncthreads();                                   // everyone is done with buf[s]
+    if (threadIdx.x == 0 && h + SS_ST < H) {
+      mbar_expect_tx(&full[s], bytes);
+      tma_load_1d(reinterpret_cast<unsigned char*>(bufs) + s * buf_bytes, preds + ((size_t)(h + SS_ST) * N + n0) * C, bytes,
+                  &full[s]);
+    }
+  }
+  {
+    uint16_t* dst = hard + (size_t)n0 * H;
+    for (int i = threadIdx.x; i < tn * H; i += blockDim.x) dst[i] = hard_t[i];
+  }
+  const float fH = (float)H;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int p = warp + 8 * r;
+    if (p >= tn) continue;
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+      const int c = lane + 32 * k;
+      if (c < C) {
+        if (ens_out) ens_out[(size_t)(n0 + p) * C + c] = ens[r][k];
+        const float v = ens[r][k] / fH;              // util.py:14 mean(dim=0), then coda.py:194 argmax
+        if (v > bv) { bv = v; bi = c; }
+      }
+    }
+    warp_argmax(bv, bi);
+    const uint16_t* hr = hard_t + (size_t)p * H;
+    const uint16_t h0 = hr[0];
+    int diff = 0;
+    for (int h = lane; h < H; h += 32) diff |= (hr[h] != h0);
+    diff = __any_sync(CODA_FULL, diff);
+    if (lane == 0) {
+      pseudo[n0 + p] = (bi == 0x7fffffff ? 0 : bi);
+      disagree[n0 + p] = (uint8_t)(diff ? 1 : 0);
+    }
+  }
+  if (bad) atomicOr(flags, bad);
+}
+
 extern "C" int coda_b200_scan_slab(const float* preds, int H, int64_t N, int C, uint16_t* hard, int32_t* pseudo,
                                    uint8_t* disagree, float* ens_out, uint32_t* flags, coda_stream_t stream) {
   CODA_CHECK_ARG(preds && hard && pseudo && disagree && flags, "scan_slab: null pointer");
   CODA_CHECK_ARG(H >= 1 && C >= 2 && C <= 65535 && N >= 1, "scan_slab: bad dims H=%d N=%lld C=%d", H, (long long)N, C);
+  if (C <= 128 && ((long long)N * C) % 4 == 0 && ((N % SS_TN) * C) % 4 == 0 &&
+      (reinterpret_cast<uintptr_t>(preds) & 15) == 0) {
+    const size_t buf_bytes = ((size_t)SS_TN * C * 4 + 127) / 128 * 128;
+    const size_t smem = SS_ST * buf_bytes + (((size_t)SS_TN * H * 2 + 15) / 16) * 16 + SS_ST * 8;
+    if (smem <= 200 * 1024) {
+      const long long grid = (N + SS_TN - 1) / SS_TN;
+      cudaStream_t st = as_stream(stream);
+#define LAUNCH_SS(KC)                                                                                             \
+  do {                                                                                                            \
+    CODA_CUDA_OK(cudaFuncSetAttribute(k_scan_slab_tma<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    k_scan_slab_tma<KC><<<(unsigned)grid, 256, smem, st>>>(preds, H, N, C, hard, pseudo, disagree, ens_out, flags);  \
+  } while (0)
+      if (C <= 32) LAUNCH_SS(1);
+      else if (C <= 64) LAUNCH_SS(2);
+      else if (C <= 96) LAUNCH_SS(3);
+      else LAUNCH_SS(4);
+#undef LAUNCH_SS
+      CODA_LAUNCH_OK("k_scan_slab_tma");
+      return CODA_B200_OK;
+    }
+  }
   int TN = 32;
   size_t need;
   while (true) {
@@ -134,6 +275,85 @@ __global__ void __launch_bounds__(256) k_confusion_accum(const float* __restrict
       if (v) atomicAdd(gtab + i, v);
     }
   }
+}
+
+// Class-sorted variant: `order` lists the items grouped by pseudo label, so one warp walks a run of items,
+// keeps the int64 column sums of the current class in registers (lane <-> column j) and flushes them with a
+// handful of global atomics when the class changes -- no shared-memory atomics on the slab-sized stream.
+#define CS_RUN 256
+template <int KC>
+__global__ void __launch_bounds__(256) k_confusion_sorted(const float* __restrict__ preds,
+                                                          const int32_t* __restrict__ pseudo,
+                                                          const int32_t* __restrict__ order, int H, long long N, int C,
+                                                          float fxs, unsigned long long* __restrict__ conf_fx) {
+  const int h = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long i0 = ((long long)blockIdx.x * 8 + warp) * CS_RUN;
+  const long long i1 = min(N, i0 + CS_RUN);
+  if (i0 >= N) return;
+  const float* slab = preds + (size_t)h * N * C;
+  unsigned long long* tab = conf_fx + (size_t)h * C * C;
+  long long acc[KC];
+#pragma unroll
+  for (int k = 0; k < KC; ++k) acc[k] = 0;
+  int cur = -1;
+  auto flush = [&]() {
+    if (cur < 0) return;
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+      const int j = lane + 32 * k;
+      if (j < C && acc[k]) atomicAdd(tab + (size_t)cur * C + j, (unsigned long long)acc[k]);
+      acc[k] = 0;
+    }
+  };
+  for (long long i = i0; i < i1; i += 4) {
+    int n[4], y[4];
+    float v[4][KC];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const long long ii = min(i + q, i1 - 1);
+      n[q] = order[ii];
+      y[q] = pseudo[n[q]];
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float* row = slab + (size_t)n[q] * C;
+#pragma unroll
+      for (int k = 0; k < KC; ++k) {
+        const int j = lane + 32 * k;
+        v[q][k] = j < C ? __ldg(row + j) : 0.f;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (i + q >= i1) break;
+      if (y[q] != cur) {
+        flush();
+        cur = y[q];
+      }
+#pragma unroll
+      for (int k = 0; k < KC; ++k) acc[k] += to_fx(v[q][k], fxs);
+    }
+  }
+  flush();
+}
+
+extern "C" int coda_b200_confusion_sorted(const float* preds, const int32_t* pseudo, const int32_t* order, int H,
+                                          int64_t N, int C, int fx_shift, int64_t* conf_fx, coda_stream_t stream) {
+  CODA_CHECK_ARG(preds && pseudo && order && conf_fx, "confusion_sorted: null pointer");
+  CODA_CHECK_ARG(fx_shift >= 8 && fx_shift <= 46, "confusion_sorted: bad fx_shift %d", fx_shift);
+  CODA_CHECK_ARG(C <= 128, "confusion_sorted: C=%d > 128 (use confusion_accum)", C);
+  const long long runs = (N + CS_RUN - 1) / CS_RUN;
+  dim3 grid((unsigned)((runs + 7) / 8), (unsigned)H);
+  const float fxs = exp2f((float)fx_shift);
+  unsigned long long* out = reinterpret_cast<unsigned long long*>(conf_fx);
+  cudaStream_t st = as_stream(stream);
+  if (C <= 32) k_confusion_sorted<1><<<grid, 256, 0, st>>>(preds, pseudo, order, H, N, C, fxs, out);
+  else if (C <= 64) k_confusion_sorted<2><<<grid, 256, 0, st>>>(preds, pseudo, order, H, N, C, fxs, out);
+  else if (C <= 96) k_confusion_sorted<3><<<grid, 256, 0, st>>>(preds, pseudo, order, H, N, C, fxs, out);
+  else k_confusion_sorted<4><<<grid, 256, 0, st>>>(preds, pseudo, order, H, N, C, fxs, out);
+  CODA_LAUNCH_OK("k_confusion_sorted");
+  return CODA_B200_OK;
 }
 
 extern "C" int coda_b200_confusion_accum(const float* preds, const int32_t* pseudo, int H, int64_t N, int C,
@@ -441,35 +661,88 @@ __global__ void __launch_bounds__(256) k_label_terms(const int32_t* __restrict__
   __syncthreads();
   const int tp = s_tp, M = s_m;
   const bool ens = have_ens && 2 * M < H;
-  if (threadIdx.x == 0) {
-    int k = 0;
-    auto emit = [&](int h, int j, float sign) {
+  // every model contributes 1 (direct), or 0 / 2 (ensemble shortcut) terms: exclusive scan over models, in order
+  __shared__ int wtot[8];
+  __shared__ int s_total;
+  int carry = 0;
+  for (int h0 = 0; h0 < H; h0 += 256) {
+    const int h = h0 + threadIdx.x;
+    const int j = h < H ? jvec[h] : 0;
+    const int n = h < H ? (ens ? (j != tp ? 2 : 0) : 1) : 0;
+    int incl = n;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(CODA_FULL, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) wtot[warp] = incl;
+    __syncthreads();
+    int off = carry;
+    for (int w = 0; w < warp; ++w) off += wtot[w];
+    int k = off + incl - n;
+    if (n) {
       const int slot = slot_of_model ? slot_of_model[h] : -1;
-      if (slot >= 0) {
-        toff[k] = shadow_off + ((long long)slot * C + j) * N;
-        tstr[k] = 1;
-      } else {
-        toff[k] = (long long)h * N * C + j;
-        tstr[k] = C;
-      }
-      tsg[k] = sign;
-      ++k;
-    };
-    for (int h = 0; h < H; ++h) {
-      const int j = jvec[h];
-      if (!ens) {
-        emit(h, j, 1.f);
-      } else if (j != tp) {
-        emit(h, j, 1.f);
-        emit(h, tp, -1.f);
+      const long long base = slot >= 0 ? shadow_off + (long long)slot * C * N : (long long)h * N * C;
+      const long long mul = slot >= 0 ? N : 1;      // shadow: [slot][class][item]; reference layout: [model][item][class]
+      const int str = slot >= 0 ? 1 : C;
+      toff[k] = base + (long long)j * mul; tstr[k] = str; tsg[k] = 1.f;
+      if (n == 2) {
+        toff[k + 1] = base + (long long)tp * mul; tstr[k + 1] = str; tsg[k + 1] = -1.f;
       }
     }
-    hdr[0] = k;
+    if (threadIdx.x == 255) s_total = off + incl;
+    __syncthreads();
+    carry = s_total;
+  }
+  if (threadIdx.x == 0) {
+    hdr[0] = carry;
     hdr[1] = ens ? tp : -1;
   }
 }
 
+// register variant of row_accumulate for C <= 32 * KC: NR rows per call (all loads issued before the first
+// reduction), the int64 column sums stay in registers
+template <int KC, int NR>
+__device__ __forceinline__ void rows_accumulate_reg(float* __restrict__ U, long long row0, int nrows, int rstride,
+                                                    int C, int lane, float fxs, int t,
+                                                    const float* __restrict__ delta, int d0,
+                                                    long long (&racc)[KC], uint32_t& bad) {
+  float u[NR][KC];
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+    const bool ok = r * rstride < nrows;
+    const float* urow = U + (size_t)(row0 + (ok ? r * rstride : 0)) * C;
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+      const int c = lane + 32 * k;
+      u[r][k] = (ok && c < C) ? urow[c] : 0.f;
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+    if (r * rstride >= nrows) break;
+    float* urow = U + (size_t)(row0 + r * rstride) * C;
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+      const int c = lane + 32 * k;
+      if (c == t) {
+        u[r][k] += delta[d0 + r * rstride];
+        urow[c] = u[r][k];
+      }
+      s += u[r][k];
+    }
+    s = warp_sum(s);
+    if (!isfinite(s)) bad |= CODA_B200_FLAG_NONFINITE_PI;
+    const float den = fmaxf(s, 1e-12f);                             // coda.py:230 clamp_(min=1e-12)
+#pragma unroll
+    for (int k = 0; k < KC; ++k) racc[k] += to_fx(u[r][k] / den, fxs);
+  }
+}
+
 #define R1_TN 256
+template <int KC>
 __global__ void __launch_bounds__(256) k_pi_rank1(const float* __restrict__ preds, const float* __restrict__ E,
                                                   long long N, int C, const long long* __restrict__ sel,
                                                   const int32_t* __restrict__ hdr, float lr, float fxs,
@@ -483,6 +756,9 @@ __global__ void __launch_bounds__(256) k_pi_rank1(const float* __restrict__ pred
   const int nt = hdr[0], tp = hdr[1];
   long long* wacc = wacc_all + (size_t)warp * C;
   for (int c = lane; c < C; c += 32) wacc[c] = 0;
+  long long racc[KC > 0 ? KC : 1];
+#pragma unroll
+  for (int k = 0; k < (KC > 0 ? KC : 1); ++k) racc[k] = 0;
   __syncthreads();
   uint32_t bad = 0;
   for (long long n0 = (long long)blockIdx.x * R1_TN; n0 < N; n0 += (long long)gridDim.x * R1_TN) {
@@ -491,20 +767,33 @@ __global__ void __launch_bounds__(256) k_pi_rank1(const float* __restrict__ pred
     if (n < N) {
       if (tp >= 0) d = __ldg(E + (size_t)n * C + tp);
       int k = 0;
-      for (; k + 8 <= nt; k += 8) {
-        float v[8];
+      for (; k + 16 <= nt; k += 16) {
+        float v[16];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) v[q] = __ldg(preds + c_toff[k + q] + n * c_tstr[k + q]);
+        for (int q = 0; q < 16; ++q) v[q] = __ldg(preds + c_toff[k + q] + n * c_tstr[k + q]);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) d = fmaf(c_tsg[k + q], v[q], d);
+        for (int q = 0; q < 16; ++q) d = fmaf(c_tsg[k + q], v[q], d);
       }
       for (; k < nt; ++k) d = fmaf(c_tsg[k], __ldg(preds + c_toff[k] + n * c_tstr[k]), d);
     }
     delta[threadIdx.x] = lr * d;
     __syncthreads();
     const int rows = (int)min((long long)R1_TN, N - n0);
-    for (int r = warp; r < rows; r += 8)
-      row_accumulate(U + (size_t)(n0 + r) * C, C, lane, fxs, t, delta[r], nullptr, wacc, bad);
+    if (KC > 0) {
+      for (int r = warp; r < rows; r += 32)     // rows r, r+8, r+16, r+24 of this warp in one batch
+        rows_accumulate_reg<(KC > 0 ? KC : 1), 4>(U, n0 + r, rows - r, 8, C, lane, fxs, t, delta, r, racc, bad);
+    } else {
+      for (int r = warp; r < rows; r += 8)
+        row_accumulate(U + (size_t)(n0 + r) * C, C, lane, fxs, t, delta[r], nullptr, wacc, bad);
+    }
+    __syncthreads();
+  }
+  if (KC > 0) {
+#pragma unroll
+    for (int k = 0; k < (KC > 0 ? KC : 1); ++k) {
+      const int c = lane + 32 * k;
+      if (c < C) wacc[c] = racc[k];
+    }
     __syncthreads();
   }
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -542,12 +831,21 @@ extern "C" int coda_b200_pi_rank1(const float* preds, const float* ens, const fl
   CODA_CUDA_OK(cudaMemcpyAsync(d_tstr, tstr, (size_t)2 * H * 4, cudaMemcpyDeviceToDevice, st));
   size_t smem = (size_t)8 * C * 8 + R1_TN * 4;
   CODA_CHECK_ARG(smem <= 200 * 1024, "pi_rank1: C=%d too large", C);
-  CODA_CUDA_OK(cudaFuncSetAttribute(k_pi_rank1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   long long want = (N + R1_TN - 1) / R1_TN;
   if (ctas_per_sm < 1 || ctas_per_sm > 8) ctas_per_sm = 8;
   int grid = (int)min(want, (long long)coda_sm_count() * ctas_per_sm);
-  k_pi_rank1<<<grid, 256, smem, st>>>(preds, ens, N, C, reinterpret_cast<const long long*>(sel), hdr, (float)lr,
-                                      exp2f((float)fx_shift), U, reinterpret_cast<unsigned long long*>(pisum_fx), flags);
+#define LAUNCH_R1(KC)                                                                                          \
+  do {                                                                                                         \
+    CODA_CUDA_OK(cudaFuncSetAttribute(k_pi_rank1<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    k_pi_rank1<KC><<<grid, 256, smem, st>>>(preds, ens, N, C, reinterpret_cast<const long long*>(sel), hdr,    \
+                                            (float)lr, exp2f((float)fx_shift), U,                              \
+                                            reinterpret_cast<unsigned long long*>(pisum_fx), flags);           \
+  } while (0)
+  if (C <= 32) LAUNCH_R1(1);
+  else if (C <= 64) LAUNCH_R1(2);
+  else if (C <= 128) LAUNCH_R1(4);
+  else LAUNCH_R1(0);
+#undef LAUNCH_R1
   CODA_LAUNCH_OK("k_pi_rank1");
   return CODA_B200_OK;
 }

@@ -49,6 +49,7 @@ __global__ void __launch_bounds__(TP_) k_beta_nodes(const float* __restrict__ D,
   __shared__ double red[8];
   __shared__ double wsum[8];
   __shared__ double pdf_sh[TP_];
+  __shared__ double lgn[3];     // lgamma(a+b) - lgamma(a) - lgamma(b) per variant: node-independent
   const int h = blockIdx.x, ci = blockIdx.y, c = cls_lo + ci, x = threadIdx.x;
   const int ncls = gridDim.y;
   const float* drow = D + ((size_t)h * C + c) * C;
@@ -67,6 +68,11 @@ __global__ void __launch_bounds__(TP_) k_beta_nodes(const float* __restrict__ D,
   const double l1x = log((double)(1.0f - xf));                    // fp32 (1 - x) as the reference forms it
   const float dxf = x > 0 ? (xf - grid_x[x - 1]) : 0.f;           // coda.py:100 (fp32 difference)
   uint32_t bad = 0;
+  if (x < 3) {
+    const float a = alpha + (x == 2 ? w : 0.f), b = beta + (x == 1 ? w : 0.f);
+    lgn[x] = lgamma((double)(a + b)) - (lgamma((double)a) + lgamma((double)b));
+  }
+  __syncthreads();
   for (int v = 0; v < 3; ++v) {
     const float a = alpha + (v == 2 ? w : 0.f);                   // coda.py:165
     const float b = beta + (v == 1 ? w : 0.f);                    // coda.py:166
@@ -74,7 +80,7 @@ __global__ void __launch_bounds__(TP_) k_beta_nodes(const float* __restrict__ D,
     const double am1 = (double)(a - 1.0f), bm1 = (double)(b - 1.0f);
     const double t1 = (am1 == 0.0) ? 0.0 : am1 * lx;              // xlogy(0, .) = 0
     const double t2 = (bm1 == 0.0) ? 0.0 : bm1 * l1x;
-    const double lp = (t1 + t2) + lgamma((double)(a + b)) - (lgamma((double)a) + lgamma((double)b));
+    const double lp = (t1 + t2) + lgn[v];
     const double pdf = exp(lp);
     if (!isfinite(pdf) || !(a > 0.f) || !(b > 0.f)) bad |= CODA_B200_FLAG_NONFINITE_TABLE;
     __syncthreads();

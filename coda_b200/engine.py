@@ -163,8 +163,14 @@ class Engine:
         H, N, C, s = self.H, self.N, self.C, self._s()
         self._call("coda_b200_scan_slab", _ptr(self.preds), H, N, C, _ptr(self.hard), _ptr(self.pseudo),
                    _ptr(self.disagree), _ptr(self.ens), _ptr(self.flags), s)
-        self._call("coda_b200_confusion_accum", _ptr(self.preds), _ptr(self.pseudo), H, N, C, self.fx_shift,
-                   _ptr(self.conf_fx), s)
+        if C <= 128:
+            order = torch.argsort(self.pseudo).to(torch.int32)      # init-time plumbing: any grouping by label will do
+            self._call("coda_b200_confusion_sorted", _ptr(self.preds), _ptr(self.pseudo), _ptr(order), H, N, C,
+                       self.fx_shift, _ptr(self.conf_fx), s)
+            del order
+        else:
+            self._call("coda_b200_confusion_accum", _ptr(self.preds), _ptr(self.pseudo), H, N, C, self.fx_shift,
+                       _ptr(self.conf_fx), s)
         self.comm.allreduce_sum_(self.conf_fx)
         self._call("coda_b200_init_dirichlets", _ptr(self.conf_fx), H, C, self.fx_shift, self.prior_strength,
                    self.multiplier, int(self.uniform_prior), _ptr(self.D), s)
@@ -233,6 +239,14 @@ class Engine:
         self._call("coda_b200_pair_fill", _ptr(self.hard), H, N, C, _ptr(self.ent_off), _ptr(self.cls_base),
                    _ptr(cursor), _ptr(self.ent_pair), _ptr(self.ent_cls), _ptr(self.zmask), _ptr(self.pair_cls),
                    _ptr(self.pair_item), s, n=2)
+        # ELL copy of the per-item lists when the longest one fits a warp (eig_points then needs no offset lookup)
+        max_cnt = int(ent_cnt.max().item()) if N else 0
+        self.ell, self.ell_k = None, 0
+        if 0 < max_cnt <= 32:
+            self.ell_k = (max_cnt + 3) // 4 * 4
+            self.ell = self._e((N, self.ell_k, 2), torch.int32)
+            self._call("coda_b200_ell_build", _ptr(self.ent_off), _ptr(self.ent_pair), _ptr(self.ent_cls), N,
+                       self.ell_k, _ptr(self.ell), s)
         self.gain = self._z((self.npairs,), torch.float32)
         self.ph_cache = self._e((self.npairs, self.Hp), torch.float32) if self.mode == "incremental" else None
 
@@ -373,7 +387,7 @@ class Engine:
             self._pair_rows(0, self.ntiles)
         self._call("coda_b200_eig_points", _ptr(self.U), N, C, _ptr(self.ent_off), _ptr(self.ent_pair),
                    _ptr(self.ent_cls), _ptr(self.gain), _ptr(self.cls_base), _ptr(self.labeled), _ptr(self.disagree),
-                   self.n_offset, _ptr(self.eig), _ptr(self.partials), _ptr(self.flags), s)
+                   self.n_offset, _ptr(self.ell), self.ell_k, _ptr(self.eig), _ptr(self.partials), _ptr(self.flags), s)
         self._call("coda_b200_select_merge", _ptr(self.partials), self.nblocks, _ptr(self.bestrec), s)
         if self.comm.world > 1:
             recs = self.comm.allgather(self.bestrec)            # (world, 5)

@@ -62,6 +62,11 @@ int coda_b200_scan_slab(const float* preds, int H, int64_t N, int C, uint16_t* h
 int coda_b200_confusion_accum(const float* preds, const int32_t* pseudo, int H, int64_t N, int C, int fx_shift,
                               int64_t* conf_fx, coda_stream_t stream);
 
+/* Same sums with the items visited in pseudo-label order (`order` = any permutation that groups equal
+ * pseudo labels; C <= 128): register accumulation, no shared-memory atomics.  Bit-identical result. */
+int coda_b200_confusion_sorted(const float* preds, const int32_t* pseudo, const int32_t* order, int H, int64_t N,
+                               int C, int fx_shift, int64_t* conf_fx, coda_stream_t stream);
+
 /* Row-normalise (coda.py:43) and build the Dirichlet prior (coda.py:46-63, 196). */
 int coda_b200_init_dirichlets(const int64_t* conf_fx, int H, int C, int fx_shift, double prior_strength,
                               double multiplier, int uniform_prior, float* D, coda_stream_t stream);
@@ -148,10 +153,14 @@ int coda_b200_pair_gain(const float* ph_cache, const uint16_t* pair_cls, int64_t
 
 /* ---- selection (coda.py:278, get_next_item_to_label coda.py:283-313) -------------------- */
 int coda_b200_eig_blocks(int64_t N); /* number of partial records eig_points writes */
+/* ell (optional): [N][ell_k] x {pair id, class} copy of the CSR lists from coda_b200_ell_build, ell_k >= the
+ * longest list and <= 32; removes one dependent load level. */
 int coda_b200_eig_points(const float* U, int64_t N, int C, const int64_t* ent_off, const int32_t* ent_pair,
                          const uint16_t* ent_cls, const float* gain, const int64_t* cls_base, const uint8_t* labeled,
-                         const uint8_t* disagree, int64_t n_offset, float* eig, int64_t* partials /*[blocks][5]*/,
-                         uint32_t* flags, coda_stream_t stream);
+                         const uint8_t* disagree, int64_t n_offset, const int32_t* ell, int ell_k, float* eig,
+                         int64_t* partials /*[blocks][5]*/, uint32_t* flags, coda_stream_t stream);
+int coda_b200_ell_build(const int64_t* ent_off, const int32_t* ent_pair, const uint16_t* ent_cls, int64_t N, int K,
+                        int32_t* ell /*[N][K][2]*/, coda_stream_t stream);
 int coda_b200_select_merge(const int64_t* recs, int nrec, int64_t* out /*[5]*/, coda_stream_t stream);
 int coda_b200_ties(const float* eig, int64_t N, const uint8_t* labeled, const uint8_t* disagree, int64_t n_offset,
                    const int64_t* best /*[5]*/, int cap, int64_t* tie_hdr /*[2]*/, int64_t* tie_idx, float* tie_val,

@@ -266,6 +266,12 @@ def test_fixed_point_sums_are_shard_invariant():
     a, _ = conf(P[:, :2300].contiguous())
     b, _ = conf(P[:, 2300:].contiguous())
     assert torch.equal(whole, a + b)
+    # the class-sorted register variant produces the same bits as the shared-memory-atomics variant
+    order = torch.argsort(pseudo).to(torch.int32)
+    sorted_out = torch.zeros_like(whole)
+    nat.check(lib.coda_b200_confusion_sorted(P.data_ptr(), pseudo.data_ptr(), order.data_ptr(), H, N, C, 40,
+                                             sorted_out.data_ptr(), st))
+    assert torch.equal(whole, sorted_out)
     ref = torch.einsum("nc,hnj->hcj", torch.nn.functional.one_hot(pseudo.long().cpu(), C).float(), preds)
     np.testing.assert_allclose((whole.double() / 2 ** 40).cpu().numpy(), ref.numpy(), rtol=2e-6, atol=1e-6)
 

@@ -163,6 +163,118 @@ __global__ void __launch_bounds__(256) k_eig_points(const float* __restrict__ U,
   if (bad) atomicOr(flags, bad);
 }
 
+// 8 lanes per item (4 items per warp instruction, IT8 batches in flight): for C <= 128 the per-item fixed cost
+// (shuffle reductions, address arithmetic) of the warp-per-item kernel above dominates, so narrower groups
+// halve the issued instructions per item.  Needs the ELL lists (ellK <= 32).
+template <int KC8>
+__global__ void __launch_bounds__(256) k_eig_points_g8(const float* __restrict__ U, long long N, int C,
+                                                       const float* __restrict__ gain,
+                                                       const long long* __restrict__ cls_base,
+                                                       const uint8_t* __restrict__ labeled,
+                                                       const uint8_t* __restrict__ disagree, long long n_offset,
+                                                       const int2* __restrict__ ell, int ellK,
+                                                       float* __restrict__ eig, long long* __restrict__ partials,
+                                                       uint32_t* __restrict__ flags) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* g0 = reinterpret_cast<float*>(smem_raw);   // [C]
+  __shared__ float sv[2][8];
+  __shared__ long long si[2][8];
+  __shared__ long long sc[8];
+  for (int c = threadIdx.x; c < C; c += blockDim.x) g0[c] = gain[cls_base[c]];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane & 7, grp = lane >> 3;
+  Best bA{-INFINITY, IDX_NONE}, bB{-INFINITY, IDX_NONE};
+  long long cntA = 0;
+  uint32_t bad = 0;
+  constexpr int IT8 = 2;
+  const long long per_iter = (long long)gridDim.x * 8 * 4 * IT8;
+  // the loop bound is warp-uniform (full-mask shuffles inside); a group past the end clamps its loads and skips its writes
+  for (long long wb = ((long long)blockIdx.x * 8 + warp) * 4 * IT8; wb < N; wb += per_iter) {
+    const long long nb = wb + grp * IT8;
+    float u[IT8][KC8];
+    int2 en[IT8][4];
+#pragma unroll
+    for (int i = 0; i < IT8; ++i) {
+      const long long n = min(nb + i, N - 1);
+      const float* urow = U + (size_t)n * C;
+#pragma unroll
+      for (int k = 0; k < KC8; ++k) {
+        const int c = g + 8 * k;
+        u[i][k] = c < C ? __ldg(urow + c) : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int e = g + 8 * j;
+        en[i][j] = e < ellK ? __ldg(ell + (size_t)n * ellK + e) : make_int2(0, -1);
+      }
+    }
+    float eg[IT8][4], eu[IT8][4];
+#pragma unroll
+    for (int i = 0; i < IT8; ++i) {
+      const long long n = min(nb + i, N - 1);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        eg[i][j] = 0.f; eu[i][j] = 0.f;
+        if (en[i][j].y >= 0) {
+          eg[i][j] = __ldg(gain + en[i][j].x);
+          eu[i][j] = __ldg(U + (size_t)n * C + en[i][j].y);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < IT8; ++i) {
+      const long long n = nb + i;
+      float s = 0.f, e = 0.f;
+#pragma unroll
+      for (int k = 0; k < KC8; ++k) {
+        const int c = g + 8 * k;
+        s += u[i][k];
+        if (c < C) e = fmaf(u[i][k], g0[c], e);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (en[i][j].y >= 0) e = fmaf(eu[i][j], eg[i][j] - g0[en[i][j].y], e);
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(CODA_FULL, s, o);
+        e += __shfl_xor_sync(CODA_FULL, e, o);
+      }
+      if (g == 0 && n < N) {
+        const float v = e / fmaxf(s, 1e-12f);                // coda.py:230, 278
+        eig[n] = v;
+        if (!isfinite(v)) bad |= CODA_B200_FLAG_NONFINITE_EIG;
+        if (!labeled[n]) {
+          best_update(bB, v, n_offset + n);
+          if (disagree[n]) {
+            best_update(bA, v, n_offset + n);
+            ++cntA;
+          }
+        }
+      }
+    }
+  }
+  best_warp(bA);
+  best_warp(bB);
+  cntA = warp_sum(cntA);
+  if (lane == 0) {
+    sv[0][warp] = bA.v; si[0][warp] = bA.i; sv[1][warp] = bB.v; si[1][warp] = bB.i; sc[warp] = cntA;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    Best a{-INFINITY, IDX_NONE}, b{-INFINITY, IDX_NONE};
+    long long cn = 0;
+    for (int w = 0; w < 8; ++w) {
+      best_update(a, sv[0][w], si[0][w]);
+      best_update(b, sv[1][w], si[1][w]);
+      cn += sc[w];
+    }
+    long long* out = partials + (size_t)blockIdx.x * 5;
+    out[0] = (long long)__float_as_int(a.v); out[1] = a.i; out[2] = cn;
+    out[3] = (long long)__float_as_int(b.v); out[4] = b.i;
+  }
+  if (bad) atomicOr(flags, bad);
+}
+
 extern "C" int coda_b200_eig_blocks(int64_t N) {
   long long want = (N + 31) / 32;
   long long cap = (long long)coda_sm_count() * 8;
@@ -180,6 +292,19 @@ extern "C" int coda_b200_eig_points(const float* U, int64_t N, int C, const int6
   CODA_CHECK_ARG(smem <= 48 * 1024, "eig_points: C=%d too large", C);
   CODA_CHECK_ARG(!ell || (ell_k >= 1 && ell_k <= 32), "eig_points: ell_k=%d out of range", ell_k);
   int grid = coda_b200_eig_blocks(N);
+  if (ell && C <= 128) {
+#define LAUNCH_G8(K8)                                                                                             \
+  k_eig_points_g8<K8><<<grid, 256, smem, as_stream(stream)>>>(                                                    \
+      U, N, C, gain, reinterpret_cast<const long long*>(cls_base), labeled, disagree, n_offset,                   \
+      reinterpret_cast<const int2*>(ell), ell_k, eig, reinterpret_cast<long long*>(partials), flags)
+    if (C <= 32) LAUNCH_G8(4);
+    else if (C <= 64) LAUNCH_G8(8);
+    else if (C <= 104) LAUNCH_G8(13);
+    else LAUNCH_G8(16);
+#undef LAUNCH_G8
+    CODA_LAUNCH_OK("k_eig_points_g8");
+    return CODA_B200_OK;
+  }
 #define LAUNCH_EP(KC)                                                                                              \
   k_eig_points<KC><<<grid, 256, smem, as_stream(stream)>>>(                                                        \
       U, N, C, reinterpret_cast<const long long*>(ent_off), ent_pair, ent_cls, gain,                               \

@@ -96,8 +96,8 @@ __global__ void __launch_bounds__(TP_) k_beta_nodes(const float* __restrict__ D,
   if (bad) atomicOr(flags, bad);
 }
 
-// grid = (ncls, HSPLIT); block = 256 threads, one per node.  CTA (ci, sl) writes dL, G0T, G1T and the raw
-// "before" integrals for the models h = sl, sl + HSPLIT, ... of class ci.
+// grid = (ncls, nsplit); block = 256 threads, one per node.  CTA (ci, sl) writes dL, G0T, G1T and the raw
+// "before" integrals for the models h = sl, sl + nsplit, ... of class ci.
 #define HSPLIT 8
 __global__ void __launch_bounds__(TP_) k_beta_combine(const double* __restrict__ pdf_s, const double* __restrict__ L_s,
                                                       const float* __restrict__ grid_x, int H, int Hp, int cls_lo,
@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(TP_) k_beta_combine(const double* __restrict__
     SB += Lb[(size_t)h * TP_ + x];
   }
   uint32_t bad = 0;
-  for (int h = blockIdx.y; h < H; h += HSPLIT) {
+  for (int h = blockIdx.y; h < H; h += gridDim.y) {
     const size_t o = (size_t)h * TP_ + x;
     const double lm = Lm[o], lh = Lh[o], lb = Lb[o];
     const double g0 = wq * pm[o] * exp(fmin(fmax(S0 - lm, -80.0), 80.0));
@@ -219,7 +219,8 @@ extern "C" int coda_b200_beta_tables(const float* D, const float* grid_x, int H,
   dim3 g1((unsigned)H, (unsigned)ncls);
   k_beta_nodes<<<g1, TP_, 0, as_stream(stream)>>>(D, grid_x, H, C, cls_lo, (float)hyp_w, seld, pdf_s, L_s, flags);
   CODA_LAUNCH_OK("k_beta_nodes");
-  dim3 g2((unsigned)ncls, HSPLIT);
+  // few classes (the per-step single-class refresh): spread the models over more CTAs
+  dim3 g2((unsigned)ncls, (unsigned)(ncls >= 16 ? HSPLIT : (H < 64 ? H : 64)));
   k_beta_combine<<<g2, TP_, 0, as_stream(stream)>>>(pdf_s, L_s, grid_x, H, Hp, cls_lo, seld, dL, G0T, G1T,
                                                     reinterpret_cast<__nv_bfloat16*>(dLb), reinterpret_cast<__nv_bfloat16*>(Gb), pb_raw, flags);
   CODA_LAUNCH_OK("k_beta_combine");

@@ -57,7 +57,7 @@ SIGNATURES = {
     "coda_b200_ell_build": (i32, [p, p, p, i64, i32, p, p]),
     "coda_b200_select_merge": (i32, [p, i32, p, p]),
     "coda_b200_ties": (i32, [p, i64, p, p, i64, p, i32, p, p, p, p]),
-    "coda_b200_device_pick": (i32, [p, p, i64, i64, p, p, p, p, i64, p]),
+    "coda_b200_device_pick": (i32, [p, p, p, i64, i64, p, p, p, p, i64, p]),
 }
 
 

@@ -412,11 +412,14 @@ extern "C" int coda_b200_ties(const float* eig, int64_t N, const uint8_t* labele
 // device-resident stand-in for `oracle(idx)` (coda/oracle.py:23-24): picks the lowest tied global
 // index (tie_hdr[1], already min-reduced across shards by the caller), looks the label up in a
 // device-resident label vector and writes the {local idx or -1, class} record the update kernels read.
-__global__ void k_device_pick(const long long* __restrict__ tie_hdr, const long long* __restrict__ labels_global,
+__global__ void k_device_pick(const long long* __restrict__ tie_hdr, const long long* __restrict__ best,
+                              const long long* __restrict__ labels_global,
                               long long n_offset, long long N, const float* __restrict__ eig,
                               long long* __restrict__ sel, long long* __restrict__ hist_idx,
                               float* __restrict__ hist_q, long long step) {
-  const long long g = tie_hdr[1];
+  // tie_hdr given: lowest index among the isclose-tied candidates; else the merged arg-max record (first index
+  // wins on exactly equal values, torch.argmax; coda.py:309)
+  const long long g = tie_hdr ? tie_hdr[1] : (best[2] > 0 ? best[1] : best[4]);
   const long long loc = g - n_offset;
   const bool own = loc >= 0 && loc < N;
   sel[0] = own ? loc : -1;
@@ -425,11 +428,12 @@ __global__ void k_device_pick(const long long* __restrict__ tie_hdr, const long 
   if (hist_q) hist_q[step] = own ? eig[loc] : 0.f;
 }
 
-extern "C" int coda_b200_device_pick(const int64_t* tie_hdr, const int64_t* labels_global, int64_t n_offset, int64_t N,
-                                     const float* eig, int64_t* sel, int64_t* hist_idx, float* hist_q, int64_t step,
-                                     coda_stream_t stream) {
-  CODA_CHECK_ARG(tie_hdr && labels_global && eig && sel, "device_pick: null pointer");
+extern "C" int coda_b200_device_pick(const int64_t* tie_hdr, const int64_t* best, const int64_t* labels_global,
+                                     int64_t n_offset, int64_t N, const float* eig, int64_t* sel, int64_t* hist_idx,
+                                     float* hist_q, int64_t step, coda_stream_t stream) {
+  CODA_CHECK_ARG((tie_hdr || best) && labels_global && eig && sel, "device_pick: null pointer");
   k_device_pick<<<1, 1, 0, as_stream(stream)>>>(reinterpret_cast<const long long*>(tie_hdr),
+                                                reinterpret_cast<const long long*>(best),
                                                 reinterpret_cast<const long long*>(labels_global), n_offset, N, eig,
                                                 reinterpret_cast<long long*>(sel),
                                                 reinterpret_cast<long long*>(hist_idx), hist_q, step);

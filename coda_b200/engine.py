@@ -47,8 +47,9 @@ class Engine:
             raise ValueError("coda_b200: preds must be contiguous (H, N, C)")
         nat.require_device()
         self.lib = nat.load()
-        if os.environ.get("CODA_B200_L2_FETCH"):
-            nat.check(self.lib.coda_b200_set_l2_fetch_granularity(int(os.environ["CODA_B200_L2_FETCH"])), "l2_fetch")
+        # sector gathers of the rank-1 refresh: ask for 64-byte L2 fills (the default 128 doubles their DRAM traffic;
+        # streaming kernels measured the same at 64 and 128)
+        nat.check(self.lib.coda_b200_set_l2_fetch_granularity(int(os.environ.get("CODA_B200_L2_FETCH", "64"))), "l2_fetch")
         self.preds = preds
         self.dev = preds.device
         self.H, self.N, self.C = (int(s) for s in preds.shape)
@@ -366,8 +367,9 @@ class Engine:
         self._mixture()
         self.scored = False
 
-    def score(self):
-        """coda.py:235-281 + 306-309: EIG of every item, candidate arg-max, isclose tie scan (enqueue only)."""
+    def score(self, ties=True):
+        """coda.py:235-281 + 306-309: EIG of every item, candidate arg-max, isclose tie scan (enqueue only).
+        ``ties=False`` (host-free loop): stop after the merged arg-max record."""
         if self.scored:
             return
         N, C, s = self.N, self.C, self._s()
@@ -392,6 +394,8 @@ class Engine:
         if self.comm.world > 1:
             recs = self.comm.allgather(self.bestrec)            # (world, 5)
             self._call("coda_b200_select_merge", _ptr(recs), self.comm.world, _ptr(self.bestrec), s)
+        if not ties:
+            return
         self._call("coda_b200_ties", _ptr(self.eig), N, _ptr(self.labeled), _ptr(self.disagree), self.n_offset,
                    _ptr(self.bestrec), TIE_CAP, _ptr(self.tie_hdr), _ptr(self.tie_idx), _ptr(self.tie_val), s, n=2)
         if self.comm.world > 1:
@@ -400,11 +404,11 @@ class Engine:
 
     def device_step(self, labels_dev: torch.Tensor, step: int, hist_idx=None, hist_q=None):
         """One acquisition step with no host round trip (bench ``value`` loop): score, pick the lowest tied
-        index, look the label up on the device (coda/oracle.py:23-24), update the posterior."""
-        self.score()
-        if self.comm.world > 1:
-            self.comm.allreduce_min_(self.tie_hdr[1:2])
-        self._call("coda_b200_device_pick", _ptr(self.tie_hdr), _ptr(labels_dev), self.n_offset, self.N,
+        index, look the label up on the device (coda/oracle.py:23-24), update the posterior.  The pick is the merged
+        arg-max record (first index wins on equal values, coda.py:309); the isclose tie rule needs the host RNG and
+        is part of the API path only."""
+        self.score(ties=False)
+        self._call("coda_b200_device_pick", None, _ptr(self.bestrec), _ptr(labels_dev), self.n_offset, self.N,
                    _ptr(self.eig), _ptr(self.sel), _ptr(hist_idx), _ptr(hist_q), int(step), self._s())
         self.post_label(device_sel=True)
 
@@ -428,7 +432,11 @@ class Engine:
                     n_ties=n_ties, tie_min=int(r[7]), tie_idx=tie_idx, tie_val=tie_val)
 
     def _fetch_sharded(self):
-        allr = self.rep_all.cpu().numpy()                       # (world, len(rep)); D2H + sync
+        if getattr(self, "rep_all_host", None) is None or self.rep_all_host.shape != self.rep_all.shape:
+            self.rep_all_host = torch.zeros(self.rep_all.shape, dtype=torch.int64).pin_memory()
+        self.rep_all_host.copy_(self.rep_all, non_blocking=True)
+        torch.cuda.current_stream(self.dev).synchronize()
+        allr = self.rep_all_host.numpy()                        # (world, len(rep))
         r0 = allr[0]
         flags = 0
         for r in allr:

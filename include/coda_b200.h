@@ -166,9 +166,9 @@ int coda_b200_ties(const float* eig, int64_t N, const uint8_t* labeled, const ui
                    const int64_t* best /*[5]*/, int cap, int64_t* tie_hdr /*[2]*/, int64_t* tie_idx, float* tie_val,
                    coda_stream_t stream);
 /* device-resident oracle stand-in (coda/oracle.py:23-24) for host-free benchmark loops. */
-int coda_b200_device_pick(const int64_t* tie_hdr, const int64_t* labels_global, int64_t n_offset, int64_t N,
-                          const float* eig, int64_t* sel, int64_t* hist_idx, float* hist_q, int64_t step,
-                          coda_stream_t stream);
+int coda_b200_device_pick(const int64_t* tie_hdr /*or NULL*/, const int64_t* best /*merged record*/,
+                          const int64_t* labels_global, int64_t n_offset, int64_t N, const float* eig, int64_t* sel,
+                          int64_t* hist_idx, float* hist_q, int64_t step, coda_stream_t stream);
 
 #ifdef __cplusplus
 }

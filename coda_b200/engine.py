@@ -260,7 +260,7 @@ class Engine:
         torch.cuda.synchronize(self.dev)
         torch.cuda.empty_cache()
         free, _total = torch.cuda.mem_get_info(self.dev)
-        reserve = int(float(os.environ.get("CODA_B200_SHADOW_RESERVE_GB", "6")) * 2 ** 30)
+        reserve = int(float(os.environ.get("CODA_B200_SHADOW_RESERVE_GB", "8")) * 2 ** 30)
         per_model = N * C * 4
         S = int(min(H, max(0, (free - reserve) // per_model)))
         cap = os.environ.get("CODA_B200_SHADOW_MODELS")

@@ -345,3 +345,44 @@ def test_tensor_core_rows_match_simt_rows(monkeypatch):
             out[tc] = (np.stack(eigs), s.get_pbest().cpu().numpy())
         np.testing.assert_allclose(out["1"][0], out["0"][0], atol=2e-7, rtol=0)
         np.testing.assert_allclose(out["1"][1], out["0"][1], atol=1e-7, rtol=0)
+
+
+def test_wide_model_axis_uses_simt_rows_and_matches_oracle():
+    """H = 300 (Hp = 320 > 256): beyond the tensor-core tile, the fp32 SIMT kernel with 10-word masks takes over."""
+    from coda_b200.synth import synth
+    preds, labels = synth(300, 260, 5, seed=13)
+    random.seed(0)
+    ora = coda_oracle.OracleSelector(preds)
+    random.seed(0)
+    sel = _mk(preds, labels)
+    assert not sel.engine.use_tc and sel.engine.W == 10
+    for _ in range(2):
+        i_ref, q_ref = ora.get_next_item_to_label()
+        i, q = sel.get_next_item_to_label()
+        np.testing.assert_allclose(sel.engine.eig.cpu().numpy()[np.asarray(ora.last_cand)], ora.last_q.numpy(), atol=EIG_ATOL)
+        assert ora.last_q.numpy()[ora.last_cand.index(i)] >= float(ora.last_q.max()) - EIG_ATOL
+        ora.add_label(i_ref, int(labels[i_ref]), q_ref)
+        sel.add_label(i_ref, int(labels[i_ref]), q)
+        np.testing.assert_allclose(sel.get_pbest().cpu().numpy(), ora.get_pbest().numpy(), atol=1e-5)
+
+
+def test_degenerate_single_model_and_two_classes():
+    """H = 1: P(best) is 1, every EIG is ~0, so every candidate ties (more than the device tie buffer holds):
+    the pick is random.choice over ALL candidates exactly like the reference (coda.py:306-311).  C = 2 is the
+    smallest class count the Dirichlet prior supports (coda.py:57 divides by C - 1)."""
+    from coda_b200.synth import synth
+    preds, labels = synth(1, 400, 2, seed=21)
+    random.seed(9)
+    ora = coda_oracle.OracleSelector(preds)
+    i_ref, q_ref = ora.get_next_item_to_label()
+    st_ref = random.getstate()
+    random.seed(9)
+    sel = _mk(preds, labels)
+    i, q = sel.get_next_item_to_label()
+    assert sel.last_report["n_ties"] == 400 and sel.stochastic and ora.stochastic
+    assert abs(q - q_ref) < EIG_ATOL and abs(q) < EIG_ATOL
+    if int(torch.isclose(ora.last_q, ora.last_q.max(), rtol=1e-8).sum()) == 400:
+        assert i == i_ref and random.getstate() == st_ref
+    np.testing.assert_allclose(sel.get_pbest().cpu().numpy(), [[1.0]], atol=1e-6)
+    sel.add_label(i, int(labels[i]), q)
+    assert int(sel.get_best_model_prediction()) == 0

@@ -635,15 +635,19 @@ extern "C" int coda_b200_shadow_build(const float* preds, int H, int64_t N, int 
 // hdr = {nterms, t' or -1}.  The term table is then copied into __constant__ memory so that the gather
 // loop reads it through the uniform/constant path instead of the LSU.
 #define R1_MAXT 2048
-__constant__ long long c_toff[R1_MAXT];   // element offset relative to preds for item 0
-__constant__ float c_tsg[R1_MAXT];
-__constant__ int c_tstr[R1_MAXT];         // element stride per item: C (reference layout) or 1 (shadow)
+struct R1Term {
+  long long off;   // element offset relative to preds for item 0
+  float sg;        // +1 / -1
+  int str;         // element stride per item: C (reference layout) or 1 (shadow)
+};
+__constant__ R1Term c_terms[R1_MAXT];
 
 __global__ void __launch_bounds__(256) k_label_terms(const int32_t* __restrict__ jvec, int H, int C, long long N,
                                                      int have_ens, const int32_t* __restrict__ slot_of_model,
                                                      long long shadow_off, int32_t* __restrict__ hdr,
-                                                     long long* __restrict__ toff, float* __restrict__ tsg,
-                                                     int* __restrict__ tstr) {
+                                                     R1Term* __restrict__ terms,
+                                                     unsigned long long* __restrict__ pisum_zero) {
+  for (int c = threadIdx.x; c < C; c += blockDim.x) pisum_zero[c] = 0ull;   // pi_rank1 accumulates into it next
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int* cnt = reinterpret_cast<int*>(smem_raw);   // [C]
   __shared__ int s_tp, s_m;
@@ -686,10 +690,8 @@ __global__ void __launch_bounds__(256) k_label_terms(const int32_t* __restrict__
       const long long base = slot >= 0 ? shadow_off + (long long)slot * C * N : (long long)h * N * C;
       const long long mul = slot >= 0 ? N : 1;      // shadow: [slot][class][item]; reference layout: [model][item][class]
       const int str = slot >= 0 ? 1 : C;
-      toff[k] = base + (long long)j * mul; tstr[k] = str; tsg[k] = 1.f;
-      if (n == 2) {
-        toff[k + 1] = base + (long long)tp * mul; tstr[k + 1] = str; tsg[k + 1] = -1.f;
-      }
+      terms[k] = R1Term{base + (long long)j * mul, 1.f, str};
+      if (n == 2) terms[k + 1] = R1Term{base + (long long)tp * mul, -1.f, str};
     }
     if (threadIdx.x == 255) s_total = off + incl;
     __syncthreads();
@@ -770,11 +772,11 @@ __global__ void __launch_bounds__(256) k_pi_rank1(const float* __restrict__ pred
       for (; k + 16 <= nt; k += 16) {
         float v[16];
 #pragma unroll
-        for (int q = 0; q < 16; ++q) v[q] = __ldg(preds + c_toff[k + q] + n * c_tstr[k + q]);
+        for (int q = 0; q < 16; ++q) v[q] = __ldg(preds + c_terms[k + q].off + n * c_terms[k + q].str);
 #pragma unroll
-        for (int q = 0; q < 16; ++q) d = fmaf(c_tsg[k + q], v[q], d);
+        for (int q = 0; q < 16; ++q) d = fmaf(c_terms[k + q].sg, v[q], d);
       }
-      for (; k < nt; ++k) d = fmaf(c_tsg[k], __ldg(preds + c_toff[k] + n * c_tstr[k]), d);
+      for (; k < nt; ++k) d = fmaf(c_terms[k].sg, __ldg(preds + c_terms[k].off + n * c_terms[k].str), d);
     }
     delta[threadIdx.x] = lr * d;
     __syncthreads();
@@ -813,22 +815,17 @@ extern "C" int coda_b200_pi_rank1(const float* preds, const float* ens, const fl
   CODA_CHECK_ARG((reinterpret_cast<uintptr_t>(terms) & 7) == 0, "pi_rank1: terms must be 8-byte aligned");
   CODA_CHECK_ARG(!shadow || slot_of_model, "pi_rank1: shadow needs slot_of_model");
   int32_t* hdr = terms;                                            // 2 ints
-  long long* toff = reinterpret_cast<long long*>(terms + 2);       // 2H int64
-  float* tsg = reinterpret_cast<float*>(toff + 2 * H);             // 2H floats
-  int* tstr = reinterpret_cast<int*>(tsg + 2 * H);                 // 2H ints
+  R1Term* tlist = reinterpret_cast<R1Term*>(terms + 2);            // 2H x 16 bytes
   CODA_CHECK_ARG((size_t)C * 4 <= 48 * 1024, "pi_rank1: C=%d too large", C);
   cudaStream_t st = as_stream(stream);
   const long long shadow_off = shadow ? (long long)(shadow - preds) : 0;   // both 4-byte aligned device pointers
   k_label_terms<<<1, 256, (size_t)C * 4, st>>>(jvec, H, C, (long long)N, ens != nullptr,
-                                                shadow ? slot_of_model : nullptr, shadow_off, hdr, toff, tsg, tstr);
+                                                shadow ? slot_of_model : nullptr, shadow_off, hdr, tlist,
+                                                reinterpret_cast<unsigned long long*>(pisum_fx));
   CODA_LAUNCH_OK("k_label_terms");
-  void *d_toff = nullptr, *d_tsg = nullptr, *d_tstr = nullptr;
-  CODA_CUDA_OK(cudaGetSymbolAddress(&d_toff, c_toff));
-  CODA_CUDA_OK(cudaGetSymbolAddress(&d_tsg, c_tsg));
-  CODA_CUDA_OK(cudaGetSymbolAddress(&d_tstr, c_tstr));
-  CODA_CUDA_OK(cudaMemcpyAsync(d_toff, toff, (size_t)2 * H * 8, cudaMemcpyDeviceToDevice, st));
-  CODA_CUDA_OK(cudaMemcpyAsync(d_tsg, tsg, (size_t)2 * H * 4, cudaMemcpyDeviceToDevice, st));
-  CODA_CUDA_OK(cudaMemcpyAsync(d_tstr, tstr, (size_t)2 * H * 4, cudaMemcpyDeviceToDevice, st));
+  static thread_local void* d_terms = nullptr;
+  if (!d_terms) CODA_CUDA_OK(cudaGetSymbolAddress(&d_terms, c_terms));
+  CODA_CUDA_OK(cudaMemcpyAsync(d_terms, tlist, (size_t)2 * H * sizeof(R1Term), cudaMemcpyDeviceToDevice, st));
   size_t smem = (size_t)8 * C * 8 + R1_TN * 4;
   CODA_CHECK_ARG(smem <= 200 * 1024, "pi_rank1: C=%d too large", C);
   long long want = (N + R1_TN - 1) / R1_TN;

@@ -71,9 +71,12 @@ class Engine:
             raise NotImplementedError("coda_b200: C > 4096 classes is not supported yet")
         self.fx_shift = max(8, min(40, 62 - math.ceil(math.log2(self.n_global + 1))))
         self.counters = {"launches": 0}
-        # side-stream refresh of the class-t tables/rows concurrently with the marginal pass: measured neutral on
-        # B200 (both kernels want the same SMs), so off by default; CODA_B200_OVERLAP=1 enables it.
-        self.overlap = os.environ.get("CODA_B200_OVERLAP", "0") == "1"
+        # side-stream refresh of the class-t tables/rows concurrently with the marginal pass.  On a full-size shard
+        # both want every SM (the tensor-core CTAs take a whole SM's shared memory) and the overlap is neutral; on
+        # small shards (multi-GPU) the few row tiles leave most SMs to the marginal pass and the two overlap.
+        # CODA_B200_OVERLAP=0/1 forces it; default: decided after the pair structure is known (see _build_pairs).
+        self.overlap_env = os.environ.get("CODA_B200_OVERLAP")
+        self.overlap = self.overlap_env == "1"
         self.profile, self.profile_only = None, None
         with torch.cuda.device(self.dev):
             self._alloc_static()
@@ -231,6 +234,8 @@ class Engine:
         self.tile_off_host = tile_off
         self.tile_off = torch.from_numpy(tile_off).to(self.dev)
         self.ntiles = int(tile_off[-1])
+        if self.overlap_env is None:    # measured: +5 % at 2 GPUs, neutral on one full-size shard
+            self.overlap = self.comm.world > 1 or self.max_cls_tiles * 2 <= int(self.lib.coda_b200_sm_count())
         self.ent_pair = self._e((max(1, n_ent),), torch.int32)
         self.ent_cls = self._e((max(1, n_ent),), torch.int16)
         self.zmask = self._e((self.npairs, W), torch.int32)
@@ -354,11 +359,10 @@ class Engine:
                         self._pair_rows(0, self.max_cls_tiles, gains=False, sel=True)
                     else:
                         self._pair_rows(self.tile_off_host[true_class], self.tile_off_host[true_class + 1], gains=False)
-            self.pisum.zero_()
             self._call("coda_b200_pi_rank1", _ptr(self.preds), _ptr(self.ens), _ptr(self.shadow),
                        _ptr(self.slot_of_model), H, N, C, _ptr(self.sel), _ptr(self.jvec), self.lr, self.fx_shift,
                        _ptr(self.terms), _ptr(self.U), _ptr(self.pisum), _ptr(self.flags),
-                       4 if overlap else 8, s, n=5)
+                       4 if overlap else 8, s, n=3)
             self.comm.allreduce_sum_(self.pisum)
             if overlap:
                 self.ev_join.record(self.side)

@@ -95,8 +95,10 @@ class CODA(ModelSelector):
     # -- acquisition -------------------------------------------------------------------------
     def get_next_item_to_label(self):
         """coda.py:283-313.  Returns (global item index: int, q: float)."""
+        if self.q in ("iid", "uncertainty"):
+            return self._select_ablation()                  # coda.py:287-295
         if self.q != "eig":
-            raise NotImplementedError(self.q)               # coda.py:297 (ablations are not on the hot path)
+            raise NotImplementedError(self.q)               # coda.py:297
         eng = self.engine
         eng.score()
         if self.prefilter_n:
@@ -123,6 +125,38 @@ class CODA(ModelSelector):
         if not bool(m.any()):
             m = eng.labeled == 0                            # coda.py:239 `or self.unlabeled_idxs`
         return m
+
+    def _select_ablation(self):
+        """coda.py:287-295: the two ablation acquisitions of the paper (random / ensemble-entropy sampling) followed by
+        the same tie rule (coda.py:306-313).  Cold path: a few torch ops on vectors the kernels already produced
+        (``ens`` = sum_h preds from the slab scan), nothing slab-sized."""
+        eng = self.engine
+        if eng.comm.world > 1:
+            raise NotImplementedError(f"q={self.q!r} with a sharded slab")
+        if self.prefilter_n:
+            raise NotImplementedError(f"q={self.q!r} together with prefilter_n")
+        mask = self._candidate_mask()
+        n = int(mask.sum())
+        if n == 0:
+            raise RuntimeError("no unlabeled items left to select from")
+        if self.q == "iid":
+            qv = torch.full((eng.N,), np.float32(1.0 / n).item(), dtype=torch.float32, device=eng.dev)
+        else:
+            if getattr(self, "_ens_entropy", None) is None:      # non-adaptive: computed once (uncertainty.py:6-11)
+                if eng.ens is None:
+                    raise RuntimeError("q='uncertainty' needs the ensemble sums (CODA_B200_ENS=0 disables them)")
+                mean = eng.ens / float(eng.H)
+                self._ens_entropy = -(mean * torch.log(mean + 1e-8)).sum(-1)
+            qv = self._ens_entropy
+        best = qv[mask].max()
+        ties = torch.isclose(qv, best, rtol=1e-8) & mask        # coda.py:307
+        nt = int(ties.sum())
+        if nt > 1:                                              # coda.py:308-311
+            idx = random.choice(torch.nonzero(ties, as_tuple=True)[0].tolist())
+            self.stochastic = True
+        else:
+            idx = int(torch.nonzero(ties, as_tuple=True)[0][0])
+        return idx, float(qv[idx])
 
     def _select_many_ties(self, rep):
         """More than TIE_CAP isclose-ties: evaluate the tie rule on the full vector (cold path)."""

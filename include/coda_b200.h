@@ -98,7 +98,8 @@ int coda_b200_shadow_build(const float* preds, int H, int64_t N, int C, const in
  * then the same normalise + column sums as pi_reduce.  With ens != NULL (scan_slab's ens_out) the sum over
  * models is taken as E[n][t'] + corrections for the models that disagree with the majority class t' of
  * jvec (exact algebra, fewer gathers).  shadow/slot_of_model (optional): models with slot_of_model[h] >= 0
- * are read from the shadow copy.  terms: int32 scratch [2 + 8*H], 8-byte aligned.  ctas_per_sm (1..8)
+ * are read from the shadow copy.  terms: int32 scratch [2 + 8*H], 8-byte aligned.  pisum_fx is ZEROED and then
+ * accumulated into (one shard's sums).  ctas_per_sm (1..8)
  * bounds the grid so a concurrent stream keeps SM resources. */
 int coda_b200_pi_rank1(const float* preds, const float* ens, const float* shadow, const int32_t* slot_of_model, int H,
                        int64_t N, int C, const int64_t* sel, const int32_t* jvec, double lr, int fx_shift,

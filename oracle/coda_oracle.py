@@ -214,11 +214,20 @@ class OracleSelector:
         return torch.cat(out) if out else torch.zeros(0)
 
     def get_next_item_to_label(self):
-        """coda.py:283-313 (q='eig' only; the ablation acquisitions are not on the hot path)."""
-        if self.q != "eig":
+        """coda.py:283-313, including the two ablation acquisitions (coda.py:287-295)."""
+        if self.q == "eig":
+            cand = self.candidates()
+            qv = self.eig_scores(cand)
+        elif self.q == "iid":                                                   # coda.py:287-290
+            cand = self.candidates()
+            qv = 1 / len(cand) * torch.ones(len(cand))
+        elif self.q == "uncertainty":                                           # coda.py:291-295, baselines/uncertainty.py:6-11
+            cand = self.candidates()
+            mean = self.preds.mean(dim=0)
+            ent = -torch.sum(mean * torch.log(mean + 1e-8), dim=-1)
+            qv = ent[cand]
+        else:
             raise NotImplementedError(self.q)
-        cand = self.candidates()
-        qv = self.eig_scores(cand)
         self.last_q, self.last_cand = qv, cand
         best = qv.max()
         ties = torch.isclose(qv, best, rtol=1e-8)                               # coda.py:307 (atol default 1e-8, trap T6)

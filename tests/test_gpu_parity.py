@@ -386,3 +386,25 @@ def test_degenerate_single_model_and_two_classes():
     np.testing.assert_allclose(sel.get_pbest().cpu().numpy(), [[1.0]], atol=1e-6)
     sel.add_label(i, int(labels[i]), q)
     assert int(sel.get_best_model_prediction()) == 0
+
+
+@pytest.mark.parametrize("q", ["iid", "uncertainty"])
+def test_ablation_acquisitions_match_oracle(q):
+    """coda.py:287-295: q='iid' / q='uncertainty' (paper ablation 2) with the reference's tie rule and RNG use."""
+    from coda_b200.synth import synth
+    preds, labels = synth(12, 500, 6, seed=17)
+    random.seed(4)
+    ora = coda_oracle.OracleSelector(preds, q=q)
+    random.seed(4)
+    sel = _mk(preds, labels, q=q)
+    for _ in range(4):
+        st = random.getstate()
+        i_ref, q_ref = ora.get_next_item_to_label()
+        after = random.getstate()
+        random.setstate(st)
+        i, qq = sel.get_next_item_to_label()
+        assert i == i_ref and abs(qq - q_ref) < 1e-6 and random.getstate() == after
+        ora.add_label(i, int(labels[i]), q_ref)
+        sel.add_label(i, int(labels[i]), qq)
+        assert int(ora.get_best_model_prediction()) == int(sel.get_best_model_prediction())
+    assert sel.stochastic == ora.stochastic

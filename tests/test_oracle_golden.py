@@ -65,3 +65,50 @@ def test_error_behaviour_matches_reference():
     bad = torch.tensor([[float("nan"), 1.0]])
     with pytest.raises(RuntimeError, match="NUMERIC ERROR"):
         coda_oracle.pbest_rows(bad, torch.ones(1, 2))
+
+
+@pytest.mark.parametrize("q", ["iid", "uncertainty"])
+def test_oracle_ablation_acquisitions_vs_live_reference(q):
+    """No golden for the ablation acquisitions: compare with the reference itself where it is mounted
+    (build container only; skipped on the GPU box)."""
+    import os
+    import sys
+    import types
+    ref = os.environ.get("CODA_REFERENCE_PATH", "/root/reference")
+    if not os.path.isdir(os.path.join(ref, "coda")):
+        pytest.skip("reference checkout not available")
+    from coda_b200.synth import synth
+    saved = {k: v for k, v in sys.modules.items() if k == "coda" or k.startswith("coda.")}
+    for k in saved:
+        del sys.modules[k]
+    for name in ("matplotlib", "matplotlib.pyplot"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.path.insert(0, ref)
+    try:
+        import coda.coda as ref_coda
+        assert ref_coda.__file__.startswith(ref)
+        preds, labels = synth(12, 500, 6, seed=17)
+
+        class DS:
+            pass
+        ds = DS()
+        ds.preds, ds.labels, ds.device = preds, labels, preds.device
+        random.seed(4)
+        r = ref_coda.CODA(ds, q=q)
+        random.seed(4)
+        o = coda_oracle.OracleSelector(preds, q=q)
+        for _ in range(4):
+            st = random.getstate()
+            ir, qr = r.get_next_item_to_label()
+            after = random.getstate()
+            random.setstate(st)
+            io, qo = o.get_next_item_to_label()
+            assert (io, random.getstate()) == (ir, after) and abs(qo - qr) < 1e-7
+            r.add_label(ir, int(labels[ir]), qr)
+            o.add_label(io, int(labels[io]), qo)
+            assert int(r.get_best_model_prediction()) == int(o.get_best_model_prediction())
+    finally:
+        sys.path.remove(ref)
+        for k in [k for k in sys.modules if k == "coda" or k.startswith("coda.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)

@@ -34,6 +34,26 @@ class TensorDataset:
         self.n_global = preds.shape[1] if n_global is None else n_global
 
 
+class ShardedFileDataset(TensorDataset):
+    """This rank's contiguous N-range of an (H, N, C) ``.pt`` slab, read through ``torch.load(mmap=True)`` so that
+    no rank ever materialises the whole tensor (the reference loader, coda/datasets.py:14, loads all of it onto
+    one device).  Labels (``*_labels.pt``, N int64) are small and replicated."""
+
+    def __init__(self, filepath, device, rank=0, world=1):
+        full = torch.load(filepath, map_location="cpu", mmap=True, weights_only=True)
+        if full.dim() != 3:
+            raise ValueError(f"{filepath}: expected an (H, N, C) tensor, got shape {tuple(full.shape)}")
+        n = int(full.shape[1])
+        lo, hi = shard_range(n, rank, world)
+        preds = full[:, lo:hi].float().contiguous().to(device)     # avoid fp16 precision errors (coda/datasets.py:14)
+        labels = None
+        label_p = filepath.replace(".pt", "_labels.pt")
+        if os.path.exists(label_p):
+            labels = torch.load(label_p, map_location="cpu", weights_only=True)
+        super().__init__(preds, labels, n_offset=lo, n_global=n)
+        self.labels_host = labels
+
+
 class SyntheticDataset(TensorDataset):
     """This rank's shard of the synthetic task; labels are replicated (N int64)."""
 

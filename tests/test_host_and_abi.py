@@ -128,3 +128,20 @@ def test_sharded_exchanges_world2_gloo():
         assert merged == (0.25, 5, 3, 0.5, 3)
         assert jvec == [3, 1, 4, 1, 5]
         assert pis == [2 ** 41 + 1, 10] and mn == 100
+
+
+def test_sharded_file_dataset_reads_only_its_range(tmp_path):
+    from coda_b200 import ShardedFileDataset
+    from coda_b200.synth import shard_range, synth
+    preds, labels = synth(5, 333, 4, seed=2)
+    f = str(tmp_path / "task.pt")
+    torch.save(preds.half(), f)                      # the loader forces fp32 like coda/datasets.py:14
+    torch.save(labels, f.replace(".pt", "_labels.pt"))
+    parts = []
+    for r in range(3):
+        ds = ShardedFileDataset(f, "cpu", rank=r, world=3)
+        lo, hi = shard_range(333, r, 3)
+        assert (ds.n_offset, ds.n_global, ds.preds.shape[1]) == (lo, 333, hi - lo)
+        assert ds.preds.dtype == torch.float32 and ds.preds.is_contiguous() and torch.equal(ds.labels, labels)
+        parts.append(ds.preds)
+    assert torch.equal(torch.cat(parts, 1), preds.half().float())

@@ -408,3 +408,43 @@ def test_ablation_acquisitions_match_oracle(q):
         sel.add_label(i, int(labels[i]), qq)
         assert int(ora.get_best_model_prediction()) == int(sel.get_best_model_prediction())
     assert sel.stochastic == ora.stochastic
+
+
+def test_main_py_loop_through_the_coda_shim(tmp_path):
+    """The reference driver's loop (main.py:55-105: seed_all, true_losses, regret bookkeeping, the four calls per
+    step) written against the `coda` shim exactly as main.py imports it, on a CUDA dataset loaded from disk;
+    the regret trajectory must equal the one the CPU oracle produces."""
+    import argparse
+    from coda import CODA
+    from coda.datasets import Dataset
+    from coda.options import LOSS_FNS
+    from coda.oracle import Oracle
+    from coda_b200.synth import synth
+    preds, labels = synth(16, 1500, 8, seed=23)
+    torch.save(preds, str(tmp_path / "toy.pt"))
+    torch.save(labels, str(tmp_path / "toy_labels.pt"))
+    args = argparse.Namespace(prefilter_n=0, alpha=0.9, learning_rate=0.01, multiplier=2.0, no_diag_prior=False, q="eig",
+                              iters=6)
+    dataset = Dataset(str(tmp_path / "toy.pt"), device=torch.device("cuda:0"))          # main.py:114
+    oracle = Oracle(dataset, loss_fn=LOSS_FNS["acc"])                                   # main.py:117-118
+    random.seed(0); np.random.seed(0); torch.manual_seed(0)                             # main.py:19-26
+    true_losses = oracle.true_losses(dataset.preds)                                     # main.py:57
+    best_loss = min(true_losses)
+    selector = CODA.from_args(dataset, args)                                            # main.py:67
+    regrets = [float(true_losses[selector.get_best_model_prediction()] - best_loss)]   # main.py:83-84
+    for _ in range(args.iters):                                                         # main.py:89-103
+        chosen_idx, selection_prob = selector.get_next_item_to_label()
+        true_class = oracle(chosen_idx)
+        selector.add_label(chosen_idx, true_class, selection_prob)
+        regrets.append(float(true_losses[selector.get_best_model_prediction()] - best_loss))
+    # the same loop on the CPU oracle
+    random.seed(0)
+    ora = coda_oracle.OracleSelector(preds)
+    tl = (1 - (preds.argmax(-1) == labels[None]).float()).mean(1)
+    ref = [float(tl[ora.get_best_model_prediction()] - tl.min())]
+    for _ in range(args.iters):
+        i, q = ora.get_next_item_to_label()
+        ora.add_label(i, int(labels[i]), q)
+        ref.append(float(tl[ora.get_best_model_prediction()] - tl.min()))
+    np.testing.assert_allclose(regrets, ref, atol=1e-6)
+    assert selector.labeled_idxs == ora.labeled_idxs and selector.stochastic == ora.stochastic

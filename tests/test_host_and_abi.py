@@ -145,3 +145,45 @@ def test_sharded_file_dataset_reads_only_its_range(tmp_path):
         assert ds.preds.dtype == torch.float32 and ds.preds.is_contiguous() and torch.equal(ds.labels, labels)
         parts.append(ds.preds)
     assert torch.equal(torch.cat(parts, 1), preds.half().float())
+
+
+def test_ctypes_signatures_match_header_arity():
+    """Every declaration in include/coda_b200.h and its ctypes binding take the same number of arguments."""
+    from coda_b200 import _native as nat
+    hdr = open(os.path.join(ROOT, "include", "coda_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    for name, (_res, args) in nat.SIGNATURES.items():
+        m = re.search(r"\b" + name + r"\s*\(([^;]*?)\)\s*;", hdr, flags=re.S)
+        assert m, name
+        params = m.group(1).strip()
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        assert n == len(args), (name, n, len(args))
+
+
+def test_reference_main_py_resolves_to_this_package(tmp_path):
+    """INTEGRATION.md section 1, as far as a GPU-less box can check it: the reference's unmodified main.py, run with this
+    repository first on PYTHONPATH, imports OUR coda package, loads the task through our Dataset / Oracle / LOSS_FNS and
+    reaches CODA.from_args -- where the missing GPU is reported loudly instead of falling back to a CPU path."""
+    import subprocess
+    import sys
+    ref = os.environ.get("CODA_REFERENCE_PATH", "/root/reference")
+    if not os.path.exists(os.path.join(ref, "main.py")):
+        pytest.skip("reference checkout not available")
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: main.py would run to completion")
+    from coda_b200.synth import synth
+    preds, labels = synth(6, 200, 4, seed=1)
+    torch.save(preds, str(tmp_path / "toy.pt"))
+    torch.save(labels, str(tmp_path / "toy_labels.pt"))
+    stubs = tmp_path / "stubs"
+    (stubs / "mlflow").mkdir(parents=True)
+    (stubs / "mlflow" / "__init__.py").write_text("def set_tracking_uri(*a, **k):\n    pass\n")   # main.py:17 runs at import
+    # PYTHONSAFEPATH: keep the script's own directory (the reference checkout) off sys.path[0] so `coda` is ours
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([ROOT, str(stubs)]), CODA_REFERENCE_PATH=ref, PYTHONSAFEPATH="1")
+    r = subprocess.run([sys.executable, os.path.join(ref, "main.py"), "--task", "toy", "--data-dir", str(tmp_path),
+                        "--method", "coda", "--seeds", "1", "--iters", "2", "--no-mlflow"],
+                       capture_output=True, text=True, env=env, cwd=str(tmp_path), timeout=300)
+    out = r.stdout + r.stderr
+    assert "Loaded preds of shape torch.Size([6, 200, 4])" in out          # our Dataset (coda/datasets.py contract)
+    assert "Best possible loss is" in out                                    # our Oracle.true_losses + LOSS_FNS['acc']
+    assert r.returncode != 0 and "no CPU path" in out, out[-2000:]          # our CODA: loud, no fallback

@@ -448,3 +448,20 @@ def test_main_py_loop_through_the_coda_shim(tmp_path):
         ref.append(float(tl[ora.get_best_model_prediction()] - tl.min()))
     np.testing.assert_allclose(regrets, ref, atol=1e-6)
     assert selector.labeled_idxs == ora.labeled_idxs and selector.stochastic == ora.stochastic
+
+
+@pytest.mark.parametrize("name", ["traj_small_h32_n3000_c10", "traj_nodiag_h10_n400_c6"])
+def test_posterior_update_is_bit_exact_given_the_reference_state(name):
+    """BASELINE configs[1] 'bit-match posterior': the construction sums differ from the reference's in summation order
+    (so D agrees to ~1e-7), but the Bayesian update itself (coda.py:316-317) is one fp32 add per model.  Seeded with the
+    reference's own initial dirichlets, every updated row must carry exactly the reference's bits, step after step."""
+    g = load_golden(name)
+    preds, labels = golden_slab(g)
+    sel = _mk(preds, labels, **g["ctor"])
+    sel.engine.D.copy_(torch.from_numpy(g["init_dirichlets"]).to(sel.engine.D.device))
+    for k in range(int(g["steps"])):
+        gi = int(g["idx"][k])
+        t = int(labels[gi])
+        sel.add_label(gi, t, 0.0)
+        assert np.array_equal(sel.dirichlets[:, t].cpu().numpy(), g["dir_row"][k]), k
+    assert np.array_equal(sel.dirichlets.cpu().numpy(), g["final_dirichlets"])

@@ -73,6 +73,13 @@ class ClockSampler:
         except Exception:
             self.p = None
 
+    def count(self):
+        try:
+            with open(self.f.name) as f:
+                return sum(1 for _ in f)
+        except Exception:
+            return 0
+
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.p is None:
@@ -128,11 +135,14 @@ def cpu_baseline(wl, seconds, seed, threads=None):
     t0 = time.perf_counter()
     cand = sel.candidates()
     t_pref = time.perf_counter() - t0
+    # the reference's loop body handles 100 items per chunk (coda.py:235); when the time budget of one sample is
+    # short the sample is a smaller batch of the same loop body (cost is linear in the items of a batch)
+    bs = coda_oracle.CHUNK if seconds >= 15 else max(4, min(coda_oracle.CHUNK, int(4 * seconds)))
     k = 0
-    while t_chunks < seconds and (k + 1) * coda_oracle.CHUNK <= len(cand):
-        ids = cand[k * coda_oracle.CHUNK:(k + 1) * coda_oracle.CHUNK]
+    while (t_chunks < seconds or k == 0) and (k + 1) * bs <= len(cand):
+        ids = cand[k * bs:(k + 1) * bs]
         t0 = time.perf_counter()
-        sel.eig_scores(ids)
+        sel.eig_scores(ids, chunk=bs)
         t_chunks += time.perf_counter() - t0
         n_items += len(ids)
         k += 1
@@ -146,7 +156,7 @@ def cpu_baseline(wl, seconds, seed, threads=None):
     step_s = (t_chunks / n_items) * (N * frac_cand) + (t_pi + t_pref) * (N / n_sub) + 2 * t_pb
     cells = n_items * C * H * coda_oracle.QUAD_NODES
     return dict(value=1.0 / step_s, unit="steps/s", cores=torch.get_num_threads(), kind="port",
-                sample=(f"extrapolated: {k} chunks x 100 items of the EIG loop ({t_chunks:.1f}s, {cells / t_chunks:.3g} cells/s) "
+                sample=(f"extrapolated: {k} chunks x {bs} items of the EIG loop ({t_chunks:.1f}s, {cells / t_chunks:.3g} cells/s) "
                         f"+ update_pi_hat + prefilter on a {n_sub}-item sub-slab, scaled to N={N}"),
                 step_seconds=step_s)
 
@@ -158,7 +168,7 @@ def run_reference(args):
     if rank != 0:
         return
     wl = WORKLOADS[args.workload]
-    per = max(3.0, min(args.cpu_seconds, 120.0 / max(1, args.steps + args.warmup)))
+    per = max(1.0, min(args.cpu_seconds, 150.0 / max(1, args.steps + args.warmup)))   # whole run: a few minutes
     vals = []
     for i in range(args.warmup + args.steps):
         r = cpu_baseline(wl, per, args.seed)
@@ -300,7 +310,6 @@ def main():
     hot = ["coda_b200_pi_rank1", "coda_b200_pair_gain", "coda_b200_pair_rows", "coda_b200_pair_rows_tc",
            "coda_b200_eig_points", "coda_b200_pi_full"]
     ms, launches, prof, picks_dev = device_loop(sel, args.warmup, args.steps, profile_only=hot)
-    clocks = sampler.stop() if sampler else {}
     value = args.steps / (ms / 1e3)
 
     # per-kernel shares over a few fully instrumented steps (not part of `value`)
@@ -308,6 +317,18 @@ def main():
 
     e2e_steps = args.e2e_steps or min(args.steps, 200)
     ms_e2e, picks_api = api_loop(sel, max(1, min(args.warmup, 3)), e2e_steps)
+    # the clock sampler has been running since before the warm-up; a very short run may end before nvidia-smi has
+    # produced samples, so keep the same load on (untimed) until a few exist
+    t_wait = time.time()
+    while True:
+        more = torch.tensor([1 if (sampler is not None and sampler.count() < 5 and time.time() - t_wait < 3.0) else 0],
+                            device=dev)
+        if world > 1:
+            dist.broadcast(more, src=0)        # every rank runs the same number of (collective) extra steps
+        if not int(more.item()):
+            break
+        device_loop(sel, 0, 20)
+    clocks = sampler.stop() if sampler else {}
     e2e = e2e_steps / (ms_e2e / 1e3)
     h2d = eng.sel_host.numel() * 8
     d2h = eng.rep_host.numel() * 8 * (world if world > 1 else 1) + 8

@@ -122,8 +122,12 @@ def cpu_baseline(wl, seconds, seed, threads=None):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import coda_oracle
     from coda_b200.synth import synth
-    if threads:
-        torch.set_num_threads(threads)
+    # the reference's ATen CPU kernels use every host core they are given; torchrun pins OMP_NUM_THREADS=1, undo that
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except Exception:
+        avail = os.cpu_count() or 1
+    torch.set_num_threads(threads or avail)
     H, N, C = wl["H"], wl["N"], wl["C"]
     n_sub = min(N, 4096)
     key = (H, N, C, seed)

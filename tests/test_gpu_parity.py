@@ -465,3 +465,25 @@ def test_posterior_update_is_bit_exact_given_the_reference_state(name):
         sel.add_label(gi, t, 0.0)
         assert np.array_equal(sel.dirichlets[:, t].cpu().numpy(), g["dir_row"][k]), k
     assert np.array_equal(sel.dirichlets.cpu().numpy(), g["final_dirichlets"])
+
+
+@pytest.mark.parametrize("C", [150, 300])
+def test_many_classes_take_the_generic_kernels(C):
+    """C > 128 leaves the register-resident fast paths (slab scan, confusion sums, rank-1 row pass, EIG assembly)
+    for their generic twins; C = 300 also overflows the shared-memory confusion table."""
+    from coda_b200.synth import synth
+    preds, labels = synth(6, 220, C, seed=31)
+    random.seed(0)
+    ora = coda_oracle.OracleSelector(preds)
+    random.seed(0)
+    sel = _mk(preds, labels)
+    np.testing.assert_allclose(sel.dirichlets.cpu().numpy(), ora.dirichlets.numpy(), rtol=3e-6, atol=1e-7)
+    for _ in range(2):
+        i_ref, q_ref = ora.get_next_item_to_label()
+        i, q = sel.get_next_item_to_label()
+        np.testing.assert_allclose(sel.engine.eig.cpu().numpy()[np.asarray(ora.last_cand)], ora.last_q.numpy(), atol=EIG_ATOL)
+        assert float(ora.last_q[ora.last_cand.index(i)]) >= float(ora.last_q.max()) - EIG_ATOL
+        ora.add_label(i_ref, int(labels[i_ref]), q_ref)
+        sel.add_label(i_ref, int(labels[i_ref]), q)
+        np.testing.assert_allclose(sel.get_pbest().cpu().numpy(), ora.get_pbest().numpy(), atol=1e-5)
+        np.testing.assert_allclose(sel.pi_hat.cpu().numpy(), ora.pi_hat.numpy(), rtol=5e-6, atol=1e-9)

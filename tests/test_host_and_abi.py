@@ -187,3 +187,53 @@ def test_reference_main_py_resolves_to_this_package(tmp_path):
     assert "Loaded preds of shape torch.Size([6, 200, 4])" in out          # our Dataset (coda/datasets.py contract)
     assert "Best possible loss is" in out                                    # our Oracle.true_losses + LOSS_FNS['acc']
     assert r.returncode != 0 and "no CPU path" in out, out[-2000:]          # our CODA: loud, no fallback
+
+
+def test_merge_rule_is_shard_count_invariant_property():
+    """hypothesis: merging per-shard arg-max records in any grouping / order gives the global record (max value,
+    lowest index on equal values, counts summed) -- what makes the selected item independent of the shard count."""
+    from hypothesis import given, settings, strategies as st
+    from coda_b200.dist import IDX_NONE, merge_records
+
+    vals = st.sampled_from([0.0, 0.125, 0.25, 0.25, 0.5])          # few distinct values -> many exact ties
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.lists(st.tuples(vals, st.booleans()), min_size=1, max_size=40), st.integers(1, 8), st.randoms())
+    def check(items, nshards, rnd):
+        # item i: value v, candidate flag a (set A = candidates, set B = all)
+        def rec(idxs):
+            va, ia, ca, vb, ib = float("-inf"), IDX_NONE, 0, float("-inf"), IDX_NONE
+            for i in idxs:
+                v, a = items[i]
+                if v > vb or (v == vb and i < ib):
+                    vb, ib = v, i
+                if a:
+                    ca += 1
+                    if v > va or (v == va and i < ia):
+                        va, ia = v, i
+            return (va, ia, ca, vb, ib)
+        whole = rec(range(len(items)))
+        bounds = sorted(rnd.sample(range(len(items) + 1), min(nshards - 1, len(items) + 1)))
+        cuts = [0] + bounds + [len(items)]
+        shards = [rec(range(cuts[k], cuts[k + 1])) for k in range(len(cuts) - 1)]
+        rnd.shuffle(shards)
+        assert merge_records(shards) == whole
+        half = len(shards) // 2                                       # tree merge == flat merge
+        assert merge_records([merge_records(shards[:half] or [shards[0]]), merge_records(shards[half:])]) == \
+            merge_records((shards[:half] or [shards[0]]) + shards[half:])
+    check()
+
+
+def test_shard_ranges_partition_the_item_axis_property():
+    from hypothesis import given, settings, strategies as st
+    from coda_b200.synth import shard_range
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.integers(0, 10 ** 7), st.integers(1, 64))
+    def check(n, world):
+        r = [shard_range(n, k, world) for k in range(world)]
+        assert r[0][0] == 0 and r[-1][1] == n
+        assert all(r[k][1] == r[k + 1][0] for k in range(world - 1))
+        sizes = [hi - lo for lo, hi in r]
+        assert max(sizes) - min(sizes) <= 1
+    check()

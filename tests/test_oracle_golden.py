@@ -112,3 +112,43 @@ def test_oracle_ablation_acquisitions_vs_live_reference(q):
         for k in [k for k in sys.modules if k == "coda" or k.startswith("coda.")]:
             del sys.modules[k]
         sys.modules.update(saved)
+
+
+def test_oracle_prefilter_subsample_vs_live_reference():
+    """coda.py:221-223 (--prefilter-n): random.sample over the candidate list, then the tie rule on the subsample --
+    checked against the reference itself where it is mounted (same RNG consumption, same pick)."""
+    import os
+    import sys
+    import types
+    ref = os.environ.get("CODA_REFERENCE_PATH", "/root/reference")
+    if not os.path.isdir(os.path.join(ref, "coda")):
+        pytest.skip("reference checkout not available")
+    from coda_b200.synth import synth
+    saved = {k: v for k, v in sys.modules.items() if k == "coda" or k.startswith("coda.")}
+    for k in saved:
+        del sys.modules[k]
+    for name in ("matplotlib", "matplotlib.pyplot"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.path.insert(0, ref)
+    try:
+        import coda.coda as ref_coda
+        ref_coda.tqdm = lambda it, *a, **k: it
+        preds, labels = synth(10, 600, 6, seed=8)
+
+        class DS:
+            pass
+        ds = DS()
+        ds.preds, ds.labels, ds.device = preds, labels, preds.device
+        random.seed(5)
+        r = ref_coda.CODA(ds, prefilter_n=50)
+        ir, qr = r.get_next_item_to_label()
+        after = random.getstate()
+        random.seed(5)
+        o = coda_oracle.OracleSelector(preds, prefilter_n=50)
+        io, qo = o.get_next_item_to_label()
+        assert (io, random.getstate()) == (ir, after) and abs(qo - qr) < 2e-6 and o.stochastic and r.stochastic
+    finally:
+        sys.path.remove(ref)
+        for k in [k for k in sys.modules if k == "coda" or k.startswith("coda.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)

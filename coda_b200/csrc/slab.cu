@@ -707,8 +707,7 @@ __global__ void __launch_bounds__(256) k_label_terms(const int32_t* __restrict__
 // reduction), the int64 column sums stay in registers
 template <int KC, int NR>
 __device__ __forceinline__ void rows_accumulate_reg(float* __restrict__ U, long long row0, int nrows, int rstride,
-                                                    int C, int lane, float fxs, int t,
-                                                    const float* __restrict__ delta, int d0,
+                                                    int C, int lane, float fxs, int t, const float (&dv)[NR],
                                                     long long (&racc)[KC], uint32_t& bad) {
   float u[NR][KC];
 #pragma unroll
@@ -730,7 +729,7 @@ __device__ __forceinline__ void rows_accumulate_reg(float* __restrict__ U, long 
     for (int k = 0; k < KC; ++k) {
       const int c = lane + 32 * k;
       if (c == t) {
-        u[r][k] += delta[d0 + r * rstride];
+        u[r][k] += dv[r];
         urow[c] = u[r][k];
       }
       s += u[r][k];
@@ -752,7 +751,6 @@ __global__ void __launch_bounds__(256) k_pi_rank1(const float* __restrict__ pred
                                                   uint32_t* __restrict__ flags) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   long long* wacc_all = reinterpret_cast<long long*>(smem_raw);                 // [8][C]
-  float* delta = reinterpret_cast<float*>(wacc_all + (size_t)8 * C);            // [R1_TN]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t = (int)sel[1];
   const int nt = hdr[0], tp = hdr[1];
@@ -763,8 +761,11 @@ __global__ void __launch_bounds__(256) k_pi_rank1(const float* __restrict__ pred
   for (int k = 0; k < (KC > 0 ? KC : 1); ++k) racc[k] = 0;
   __syncthreads();
   uint32_t bad = 0;
-  for (long long n0 = (long long)blockIdx.x * R1_TN; n0 < N; n0 += (long long)gridDim.x * R1_TN) {
-    const long long n = n0 + threadIdx.x;
+  // one warp = 32 consecutive items: lane i gathers item i's increment, then the warp walks the 32 rows of U
+  // (increment handed over by shuffle).  No block-level barrier inside the loop, warps run independently.
+  const long long wstride = (long long)gridDim.x * R1_TN;
+  for (long long n0 = (long long)blockIdx.x * R1_TN + warp * 32; n0 < N; n0 += wstride) {
+    const long long n = n0 + lane;
     float d = 0.f;
     if (n < N) {
       if (tp >= 0) d = __ldg(E + (size_t)n * C + tp);
@@ -778,17 +779,21 @@ __global__ void __launch_bounds__(256) k_pi_rank1(const float* __restrict__ pred
       }
       for (; k < nt; ++k) d = fmaf(c_terms[k].sg, __ldg(preds + c_terms[k].off + n * c_terms[k].str), d);
     }
-    delta[threadIdx.x] = lr * d;
-    __syncthreads();
-    const int rows = (int)min((long long)R1_TN, N - n0);
+    const float dl = lr * d;
+    const int rows = (int)min(32LL, N - n0);
     if (KC > 0) {
-      for (int r = warp; r < rows; r += 32)     // rows r, r+8, r+16, r+24 of this warp in one batch
-        rows_accumulate_reg<(KC > 0 ? KC : 1), 4>(U, n0 + r, rows - r, 8, C, lane, fxs, t, delta, r, racc, bad);
+      for (int r = 0; r < rows; r += 4) {
+        float dv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dv[i] = __shfl_sync(CODA_FULL, dl, (r + i) & 31);
+        rows_accumulate_reg<(KC > 0 ? KC : 1), 4>(U, n0 + r, rows - r, 1, C, lane, fxs, t, dv, racc, bad);
+      }
     } else {
-      for (int r = warp; r < rows; r += 8)
-        row_accumulate(U + (size_t)(n0 + r) * C, C, lane, fxs, t, delta[r], nullptr, wacc, bad);
+      for (int r = 0; r < rows; ++r) {
+        const float dr = __shfl_sync(CODA_FULL, dl, r);
+        row_accumulate(U + (size_t)(n0 + r) * C, C, lane, fxs, t, dr, nullptr, wacc, bad);
+      }
     }
-    __syncthreads();
   }
   if (KC > 0) {
 #pragma unroll
@@ -796,8 +801,8 @@ __global__ void __launch_bounds__(256) k_pi_rank1(const float* __restrict__ pred
       const int c = lane + 32 * k;
       if (c < C) wacc[c] = racc[k];
     }
-    __syncthreads();
   }
+  __syncthreads();          // every warp's column sums are in shared memory
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     long long s2 = 0;
     for (int w = 0; w < 8; ++w) s2 += wacc_all[(size_t)w * C + c];

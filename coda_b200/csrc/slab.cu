@@ -557,7 +557,10 @@ extern "C" int coda_b200_pi_reduce(float* U, int64_t N, int C, int fx_shift, flo
 __global__ void k_label_row(const uint16_t* __restrict__ hard, int H, long long N, const long long* __restrict__ sel,
                             int32_t* __restrict__ jvec, uint8_t* __restrict__ labeled) {
   const long long idx = sel[0];
-  if (idx < 0 || idx >= N) return;   // not owned by this shard
+  if (idx < 0 || idx >= N) {          // not owned by this shard: contribute zeros to the SUM all-reduce of jvec
+    for (int h = threadIdx.x; h < H; h += blockDim.x) jvec[h] = 0;
+    return;
+  }
   for (int h = threadIdx.x; h < H; h += blockDim.x) jvec[h] = hard[(size_t)idx * H + h];
   if (threadIdx.x == 0) labeled[idx] = 1;
 }

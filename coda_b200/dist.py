@@ -63,9 +63,7 @@ class TorchComm:
         return out
 
     def share_jvec_(self, jvec, sel):
-        """Owner holds p_h(idx) in ``jvec``; everyone else contributes zeros."""
-        own = (sel[0:1] >= 0).to(jvec.dtype)
-        jvec.mul_(own)
+        """Owner holds p_h(idx) in ``jvec``; every other rank's ``jvec`` is zero (``label_row`` wrote it that way)."""
         self.dist.all_reduce(jvec, op=self.dist.ReduceOp.SUM, group=self.group)
         return jvec
 

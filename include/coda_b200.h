@@ -84,7 +84,8 @@ int coda_b200_pi_reduce(float* U, int64_t N, int C, int fx_shift, float* xi_out,
 /* ---- posterior update (CODA.add_label, coda.py:315-319) ------------------------------- */
 /* sel = {local item index or -1 when another shard owns it, revealed class}. */
 
-/* jvec[h] = p_h(idx) (coda.py:316) and labeled[idx] = 1 (coda.py:323), owner shard only. */
+/* jvec[h] = p_h(idx) (coda.py:316) and labeled[idx] = 1 (coda.py:323) on the owner shard; jvec = 0 elsewhere,
+ * so a SUM all-reduce of jvec hands the owner's row to every shard. */
 int coda_b200_label_row(const uint16_t* hard, int H, int64_t N, const int64_t* sel, int32_t* jvec, uint8_t* labeled,
                         coda_stream_t stream);
 /* D[h][t][jvec[h]] += lr  (coda.py:317). */

@@ -103,7 +103,7 @@ def _gloo_worker(rank, world, port, q):
     allr = comm.allgather(rec)
     merged = merge_records([tuple(r.tolist()) for r in allr])
     # 2. label exchange: only the owner knows p_h(idx); SUM all-reduce with zeros elsewhere
-    jvec = torch.tensor([3, 1, 4, 1, 5], dtype=torch.int32) if rank == 1 else torch.tensor([9, 9, 9, 9, 9], dtype=torch.int32)
+    jvec = torch.tensor([3, 1, 4, 1, 5], dtype=torch.int32) if rank == 1 else torch.zeros(5, dtype=torch.int32)
     sel = torch.tensor([12 if rank == 1 else -1, 2], dtype=torch.int64)
     comm.share_jvec_(jvec, sel)
     # 3. marginals: exact int64 sums

@@ -389,7 +389,7 @@ def main():
         except Exception:
             pass
     cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:      # rank 0, N=1 only (the reference arm covers N>1)
         cpu = cpu_baseline(wl, args.cpu_seconds, args.seed)
         cpu.pop("step_seconds", None)
 

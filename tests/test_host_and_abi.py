@@ -237,3 +237,26 @@ def test_shard_ranges_partition_the_item_axis_property():
         sizes = [hi - lo for lo, hi in r]
         assert max(sizes) - min(sizes) <= 1
     check()
+
+
+def test_baseline_selectors_resolve_to_the_reference_when_pointed_at_it():
+    """coda/baselines is out of scope; with CODA_REFERENCE_PATH set the shim serves the reference's
+    own classes so `main.py --method iid|uncertainty|...` keeps working next to our CODA."""
+    import subprocess
+    import sys
+    ref = os.environ.get("CODA_REFERENCE_PATH", "/root/reference")
+    if not os.path.isdir(os.path.join(ref, "coda", "baselines")):
+        pytest.skip("reference checkout not available")
+    code = (
+        "import torch\n"
+        "from coda.baselines import IID, ActiveTesting, VMA, ModelPicker, Uncertainty\n"
+        "from coda.options import LOSS_FNS\n"
+        "from coda_b200.synth import synth\n"
+        "p, l = synth(4, 50, 3, 1)\n"
+        "class DS: pass\n"
+        "d = DS(); d.preds, d.labels, d.device = p, l, p.device\n"
+        "s = Uncertainty(d, LOSS_FNS['acc']); i, q = s.get_next_item_to_label(); s.add_label(int(i), int(l[i]), q)\n"
+        "print('OK', IID.__module__, int(s.get_best_model_prediction()))\n")
+    env = dict(os.environ, PYTHONPATH=ROOT, CODA_REFERENCE_PATH=ref)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0 and "OK coda.baselines.iid" in r.stdout, r.stdout + r.stderr[-1500:]

@@ -113,69 +113,145 @@ class ClockSampler:
 _CPU_SEL = {}
 
 
-def cpu_baseline(wl, seconds, seed, threads=None):
-    """Reference algorithm (oracle port of coda/coda.py) on the host cores, bounded sample, extrapolated.
-    A full CPU step at cfg3 is ~days (6.55e12 quadrature cells), so: time whole 100-item chunks of the EIG
-    loop (coda.py:262-279) on a 4096-item sub-slab for ~`seconds`, plus one update_pi_hat and one
-    _prefilter on the sub-slab, and scale linearly to N items (chunks are independent and equal-cost)."""
-    import torch
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import coda_oracle
-    from coda_b200.synth import synth
-    # the reference's ATen CPU kernels use every host core they are given; torchrun pins OMP_NUM_THREADS=1, undo that
+def host_cores():
+    """Cores this process may really use: min(scheduler affinity, cgroup CPU quota).  A GPU lease is often a
+    cgroup-limited slice of a big host; sizing the thread pool from the affinity mask alone oversubscribes it."""
     try:
-        avail = len(os.sched_getaffinity(0))
+        n = len(os.sched_getaffinity(0))
     except Exception:
-        avail = os.cpu_count() or 1
-    torch.set_num_threads(threads or avail)
-    H, N, C = wl["H"], wl["N"], wl["C"]
-    n_sub = min(N, 4096)
-    key = (H, N, C, seed)
-    if key not in _CPU_SEL:      # the sub-slab and the oracle state are set-up, not part of any timed sample
-        preds, labels = synth(H, N, C, seed, n_lo=0, n_hi=n_sub)
-        _CPU_SEL[key] = coda_oracle.OracleSelector(preds)
-    sel = _CPU_SEL[key]
-    t_chunks, n_items = 0.0, 0
-    t0 = time.perf_counter()
-    cand = sel.candidates()
-    t_pref = time.perf_counter() - t0
-    # the reference's loop body handles 100 items per chunk (coda.py:235); when the time budget of one sample is
-    # short the sample is a smaller batch of the same loop body (cost is linear in the items of a batch)
-    bs = coda_oracle.CHUNK if seconds >= 15 else max(4, min(coda_oracle.CHUNK, int(4 * seconds)))
-    k = 0
-    while (t_chunks < seconds or k == 0) and (k + 1) * bs <= len(cand):
-        ids = cand[k * bs:(k + 1) * bs]
+        n = os.cpu_count() or 1
+    try:                                                   # cgroup v2
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, -(-int(quota) // int(period))))
+    except Exception:
+        try:                                               # cgroup v1
+            quota = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            period = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if quota > 0:
+                n = min(n, max(1, -(-quota // period)))
+        except Exception:
+            pass
+    return max(1, n)
+
+
+def workload_string(args, wl, world):
+    return (f"synthetic M={wl['H']} N={wl['N']} C={wl['C']} ({args.workload}{', dense' if args.dense else ''}), "
+            f"N-axis sharded over {world} GPU(s)")
+
+
+class CpuReference:
+    """Reference algorithm (oracle port of coda/coda.py) on the host cores: bounded samples, extrapolated.
+
+    A full CPU step at cfg3 is ~days (6.55e12 quadrature cells), so one *sample* times the body of the EIG loop
+    (coda.py:262-279) on a small batch of candidates of a 512-item sub-slab; `update_pi_hat`, `_prefilter` and
+    `get_pbest` are timed once on the sub-slab.  Everything is scaled linearly to N items (the loop body is
+    independent per item and equal-cost).  Every sample is bounded by WALL CLOCK: the batch size is calibrated
+    from a 1-item probe so that a sample fits its time slice on whatever core budget this box grants."""
+
+    N_SUB = 512
+
+    def __init__(self, wl, seed, dense=False, threads=None):
+        import torch
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import coda_oracle
+        from coda_b200.synth import synth
+        self.torch, self.ora = torch, coda_oracle
+        self.cores = threads or host_cores()
+        torch.set_num_threads(self.cores)        # torchrun pins OMP_NUM_THREADS=1; the reference uses what it is given
+        self.H, self.N, self.C = wl["H"], wl["N"], wl["C"]
+        self.n_sub = min(self.N, self.N_SUB)
         t0 = time.perf_counter()
-        sel.eig_scores(ids, chunk=bs)
-        t_chunks += time.perf_counter() - t0
-        n_items += len(ids)
-        k += 1
-    t0 = time.perf_counter()
-    coda_oracle.consensus_marginals(sel.dirichlets, sel.preds)
-    t_pi = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    sel.get_pbest()
-    t_pb = time.perf_counter() - t0
-    frac_cand = len(cand) / n_sub
-    step_s = (t_chunks / n_items) * (N * frac_cand) + (t_pi + t_pref) * (N / n_sub) + 2 * t_pb
-    cells = n_items * C * H * coda_oracle.QUAD_NODES
-    return dict(value=1.0 / step_s, unit="steps/s", cores=torch.get_num_threads(), kind="port",
-                sample=(f"extrapolated: {k} chunks x {bs} items of the EIG loop ({t_chunks:.1f}s, {cells / t_chunks:.3g} cells/s) "
-                        f"+ update_pi_hat + prefilter on a {n_sub}-item sub-slab, scaled to N={N}"),
-                step_seconds=step_s)
+        preds, _ = synth(self.H, self.N, self.C, seed, n_lo=0, n_hi=self.n_sub, dense=dense)
+        self.sel = coda_oracle.OracleSelector(preds)
+        t1 = time.perf_counter()
+        self.cand = self.sel.candidates()
+        self.t_pref = time.perf_counter() - t1
+        t1 = time.perf_counter()
+        coda_oracle.consensus_marginals(self.sel.dirichlets, self.sel.preds)
+        self.t_pi = time.perf_counter() - t1
+        t1 = time.perf_counter()
+        self.sel.get_pbest()
+        self.t_pb = time.perf_counter() - t1
+        # probes with 1 and 3 items: the loop body costs a + b * items (a = the 255-iteration cdf loop and the other
+        # per-chunk launches, coda.py:98-101, amortised by the reference over 100 items; b = per-item arithmetic)
+        t1 = time.perf_counter()
+        self.sel.eig_scores(self.cand[:1], chunk=1)
+        p1 = time.perf_counter() - t1
+        t1 = time.perf_counter()
+        self.sel.eig_scores(self.cand[1:4], chunk=3)
+        p3 = time.perf_counter() - t1
+        self.s_per_item = max(1e-5, (p3 - p1) / 2)
+        self.s_fixed = max(0.0, p1 - self.s_per_item)
+        self.setup_s = time.perf_counter() - t0
+        self.cursor = 4
+
+    def sample(self, seconds):
+        """Time one batch of the EIG loop sized to ~`seconds`; -> dict(step_seconds, items, cells_per_s, ...)."""
+        chunk = self.ora.CHUNK
+        bs = int(max(1, min(chunk, (0.8 * seconds - self.s_fixed) / self.s_per_item, len(self.cand))))
+        if self.cursor + bs > len(self.cand):
+            self.cursor = 0
+        ids = self.cand[self.cursor:self.cursor + bs]
+        self.cursor += bs
+        t0 = time.perf_counter()
+        self.sel.eig_scores(ids, chunk=bs)
+        dt = time.perf_counter() - t0
+        per_item = (dt - self.s_fixed) / len(ids) if dt > 2 * self.s_fixed else dt / len(ids)
+        self.s_per_item = max(1e-6, per_item)
+        chunk_s = dt if len(ids) == chunk else self.s_fixed + per_item * chunk     # one 100-item chunk as the reference runs it
+        frac_cand = len(self.cand) / self.n_sub
+        step_s = chunk_s * (self.N * frac_cand / chunk) + (self.t_pi + self.t_pref) * (self.N / self.n_sub) + 2 * self.t_pb
+        cells = len(ids) * self.C * self.H * self.ora.QUAD_NODES
+        return dict(step_seconds=step_s, items=len(ids), seconds=dt, cells_per_s=cells / dt)
+
+    def describe(self, samples):
+        items = sum(s["items"] for s in samples)
+        secs = sum(s["seconds"] for s in samples)
+        cps = sum(s["cells_per_s"] * s["seconds"] for s in samples) / max(secs, 1e-9)
+        return (f"extrapolated: {len(samples)} sample(s), {items} items of the EIG loop body (coda.py:262-279) in {secs:.1f}s "
+                f"({cps:.3g} cells/s; per-chunk overhead {self.s_fixed * 1e3:.0f} ms amortised over 100 items as the reference does) "
+                f"+ update_pi_hat + prefilter + get_pbest timed once on a {self.n_sub}-item sub-slab, "
+                f"scaled linearly to N={self.N}; {self.cores} torch threads (cgroup-aware)")
+
+
+def cpu_baseline(wl, seconds, seed, dense=False):
+    """`cpu_baseline` leg of the GPU arm (rank 0, N=1): a few wall-clock-bounded samples, ~`seconds` in total."""
+    key = (wl["H"], wl["N"], wl["C"], seed, dense)
+    if key not in _CPU_SEL:
+        _CPU_SEL[key] = CpuReference(wl, seed, dense)
+    ref = _CPU_SEL[key]
+    n = 3
+    samples = [ref.sample(seconds / n) for _ in range(n)]
+    step_s = statistics.mean(s["step_seconds"] for s in samples)
+    return dict(value=1.0 / step_s, unit="steps/s", cores=ref.cores, kind="port", sample=ref.describe(samples))
+
+
+REFERENCE_BUDGET_S = 75.0     # wall-clock budget of all timed + warm-up samples of `--impl reference`
 
 
 def run_reference(args):
     """--impl reference: the reference's CPU algorithm (oracle port; the Python reference cannot travel to
-    the GPU box) on this box's host cores.  Rank 0 only."""
+    the GPU box) on this box's host cores.  Rank 0 only.  Whole run: set-up (~10-30 s) + <= REFERENCE_BUDGET_S."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     wl = WORKLOADS[args.workload]
-    per = max(1.0, min(args.cpu_seconds, 150.0 / max(1, args.steps + args.warmup)))   # whole run: a few minutes
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    t_start = time.perf_counter()
+    ref = CpuReference(wl, args.seed, args.dense)
+    n = max(1, args.warmup + args.steps)
+    per = max(0.05, min(args.cpu_seconds, REFERENCE_BUDGET_S / n))
+    deadline = t_start + ref.setup_s + REFERENCE_BUDGET_S
     vals = []
-    for i in range(args.warmup + args.steps):
-        r = cpu_baseline(wl, per, args.seed)
+    for i in range(n):
+        # never start a sample that cannot finish before the deadline: shrink it, and if nothing is left reuse the
+        # running estimate (the loop body is equal-cost per item, so a skipped sample changes nothing but noise)
+        left = deadline - time.perf_counter()
+        if left < ref.s_per_item and vals:
+            r = dict(vals[-1], items=0, seconds=0.0)
+        else:
+            r = ref.sample(min(per, max(left, ref.s_per_item)))
         if i >= args.warmup:
             vals.append(r)
     step_s = statistics.mean(v["step_seconds"] for v in vals)
@@ -184,9 +260,11 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": "steps/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"synthetic M={wl['H']} N={wl['N']} C={wl['C']} ({args.workload})", "mode": "reference-cpu"},
-        "cpu_baseline": {"value": v, "unit": "steps/s", "cores": vals[-1]["cores"], "kind": "port", "sample": vals[-1]["sample"]},
+        "config": {"workload": workload_string(args, wl, world), "mode": "reference-cpu"},
+        "cpu_baseline": {"value": v, "unit": "steps/s", "cores": ref.cores, "kind": "port",
+                         "sample": ref.describe([x for x in vals if x["items"]] or vals)},
         "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": time.perf_counter() - t_start,
     }
     print(json.dumps(line), flush=True)
 
@@ -390,8 +468,7 @@ def main():
             pass
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:      # rank 0, N=1 only (the reference arm covers N>1)
-        cpu = cpu_baseline(wl, args.cpu_seconds, args.seed)
-        cpu.pop("step_seconds", None)
+        cpu = cpu_baseline(wl, args.cpu_seconds, args.seed, args.dense)
 
     if rank == 0:
         line = {
@@ -399,7 +476,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {
-                "workload": f"synthetic M={H} N={N} C={C} ({args.workload}{', dense' if args.dense else ''}), N-axis sharded over {world} GPU(s)",
+                "workload": workload_string(args, wl, world),
                 "mode": args.mode, "l2": "per-step working set (slab gather + row cache + U) >> 126 MB L2; no flush needed",
                 "tie_rule_value": "arg-max, first index (device loop)", "tie_rule_e2e": "random.choice (coda.py:308)",
                 "pairs": npairs, "heavy_pairs": eng.n_heavy, "tensor_core_rows": bool(eng.use_tc), "entries_per_item": eng.n_entries / max(1, n_loc),

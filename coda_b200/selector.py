@@ -218,4 +218,4 @@ class CODA(ModelSelector):
     def get_best_model_prediction(self):
         """coda.py:334-346 -> 0-d LongTensor (trap T10); bumps ``step``."""
         self.step += 1
-        return self.engine.best_model[0]
+        return self.engine.best_model[0].clone()                # a fresh 0-d tensor like torch.argmax (coda.py:346)

@@ -143,5 +143,7 @@ if __name__ == "__main__":
     if "nodiag" in which:
         run_case(ref, "traj_nodiag_h10_n400_c6", 10, 400, 6, 4, steps=4,
                  ctor=dict(disable_diag_prior=1, alpha=0.8, learning_rate=0.05, multiplier=1.5))
+    if "h256" in which:   # full-width tensor-core tile (Hp = 256, C = 100): ~6 min per step on 8 cores
+        run_case(ref, "traj_h256_h256_n1500_c100", 256, 1500, 100, 5, steps=2)
     if "cfg2" in which:   # ~270 s/step on 8 cores: a few steps only
         run_case(ref, "traj_cfg2_h64_n50000_c10", 64, 50000, 10, 0, steps=3)

@@ -487,3 +487,110 @@ def test_many_classes_take_the_generic_kernels(C):
         sel.add_label(i_ref, int(labels[i_ref]), q)
         np.testing.assert_allclose(sel.get_pbest().cpu().numpy(), ora.get_pbest().numpy(), atol=1e-5)
         np.testing.assert_allclose(sel.pi_hat.cpu().numpy(), ora.pi_hat.numpy(), rtol=5e-6, atol=1e-9)
+
+
+@pytest.mark.parametrize("mode", ["incremental", "recompute"])
+@pytest.mark.parametrize("name", golden_names())
+def test_device_loop_follows_the_reference_trajectory(name, mode):
+    """The host-free loop that produces bench.py's `value` (Engine.device_step: score -> merged arg-max -> label
+    looked up on the device -> posterior update) against the reference's own free-running trajectory.  None of the
+    goldens has an isclose tie (n_ties == 1 everywhere), so arg-max-first-index IS the reference's rule
+    (coda.py:306-313) on these runs and every pick must be the reference's pick."""
+    g = load_golden(name)
+    if mode != "incremental" and int(g["N"]) > 20000:
+        pytest.skip("large golden: product mode only")
+    assert int(g["n_ties"].max()) == 1
+    preds, labels = golden_slab(g)
+    sel = _mk(preds, labels, mode=mode, **g["ctor"])
+    eng = sel.engine
+    H, K = int(g["H"]), int(g["steps"])
+    labels_dev = labels.to(eng.dev)
+    hist_idx = torch.zeros(K, dtype=torch.int64, device=eng.dev)
+    hist_q = torch.zeros(K, dtype=torch.float32, device=eng.dev)
+    for k in range(K):
+        eng.device_step(labels_dev, k, hist_idx, hist_q)
+        gi = int(g["idx"][k])
+        t = int(labels[gi])
+        assert int(hist_idx[k]) == gi, (k, hist_idx.tolist(), g["idx"].tolist())
+        assert abs(float(hist_q[k]) - float(g["q"][k])) < EIG_ATOL
+        np.testing.assert_allclose(eng.m0[:H].cpu().numpy(), g["pbest"][k], atol=1e-5)
+        np.testing.assert_allclose(eng.pi_hat.cpu().numpy(), g["pi_hat"][k], rtol=2e-6)
+        np.testing.assert_allclose(eng.D[:, t].cpu().numpy(), g["dir_row"][k], rtol=3e-7, atol=0)
+        assert int(eng.best_model[0]) == int(g["best_model"][k])
+    np.testing.assert_allclose(eng.D.cpu().numpy(), g["final_dirichlets"], rtol=2e-6, atol=1e-7)
+    assert int(eng.labeled.sum()) == K
+    eng.check_flags(sync=True)
+
+
+def test_full_width_tensor_core_tile_against_the_reference():
+    """H = 256, C = 100 (Hp = 256: 8 K-chunks, all 512 TMEM columns of k_pair_rows_tc) pinned to the reference's
+    compute_pbest_beta_batched (coda.py:77-119) through a golden generated by the reference itself -- not to the
+    SIMT twin.  Teacher-forced; EIG vector, pick, P(best), posterior rows."""
+    names = [n for n in golden_names() if "h256" in n]
+    if not names:
+        pytest.skip("h256 golden not generated")
+    g = load_golden(names[0])
+    preds, labels = golden_slab(g)
+    random.seed(0)
+    sel = _mk(preds, labels)
+    assert sel.engine.use_tc and sel.engine.Hp == 256
+    np.testing.assert_allclose(sel.get_pbest().cpu().numpy(), g["init_pbest"], atol=1e-5)
+    for k in range(int(g["steps"])):
+        idx, q = sel.get_next_item_to_label()
+        ref = g["eig"][k]
+        cand = ~np.isnan(ref)
+        np.testing.assert_allclose(sel.engine.eig.cpu().numpy()[cand], ref[cand], atol=EIG_ATOL)
+        _check_pick(ref, idx, int(g["idx"][k]))
+        gi = int(g["idx"][k])
+        sel.add_label(gi, int(labels[gi]), q)
+        assert int(sel.get_best_model_prediction()) == int(g["best_model"][k])
+        np.testing.assert_allclose(sel.get_pbest().cpu().numpy()[0], g["pbest"][k], atol=1e-5)
+        np.testing.assert_allclose(sel.pi_hat.cpu().numpy(), g["pi_hat"][k], rtol=2e-6)
+
+
+def test_back_to_back_add_label_replays_a_label_history():
+    """API-legal: several add_label calls with no get_next_item_to_label in between (replaying a label history).
+    Every call must apply ITS OWN (idx, class) -- the pinned staging of the record must not be overwritten while an
+    earlier copy is still queued behind the step kernels.  Checked against the oracle (small) and against a twin that
+    synchronises between calls (large shard, where the kernels of one label take hundreds of microseconds)."""
+    from coda_b200.synth import synth
+    preds, labels = synth(10, 400, 6, seed=8)
+    random.seed(0)
+    ora = coda_oracle.OracleSelector(preds)
+    sel = _mk(preds, labels)
+    hist = [17, 230, 5, 399, 64, 128]
+    for i in hist:
+        ora.add_label(i, int(labels[i]), 0.0)
+    for i in hist:
+        sel.add_label(i, int(labels[i]), 0.0)                 # no sync, no fetch in between
+    np.testing.assert_allclose(sel.dirichlets.cpu().numpy(), ora.dirichlets.numpy(), rtol=3e-6, atol=1e-7)
+    np.testing.assert_allclose(sel.pi_hat.cpu().numpy(), ora.pi_hat.numpy(), rtol=5e-6)
+    assert sorted(np.nonzero(sel.engine.labeled.cpu().numpy())[0].tolist()) == sorted(hist)
+    np.testing.assert_allclose(sel.get_pbest().cpu().numpy(), ora.get_pbest().numpy(), atol=1e-5)
+    preds, labels = synth(64, 300000, 16, seed=6)
+    a, b = _mk(preds, labels), _mk(preds, labels)
+    hist = [7, 150001, 299999, 31337, 8, 123456, 222222, 9]
+    for i in hist:
+        a.add_label(i, int(labels[i]), 0.0)
+    for i in hist:
+        b.add_label(i, int(labels[i]), 0.0)
+        torch.cuda.synchronize()
+    assert torch.equal(a.dirichlets, b.dirichlets) and torch.equal(a.pi_hat, b.pi_hat)
+    assert torch.equal(a.engine.labeled, b.engine.labeled) and torch.equal(a.get_pbest(), b.get_pbest())
+    ia, ib = a.get_next_item_to_label(), b.get_next_item_to_label()
+    assert ia == ib
+
+
+def test_best_model_prediction_is_a_fresh_tensor():
+    """coda.py:346 returns torch.argmax(...): a new tensor every call.  A caller keeping the result of an earlier
+    step must not see it change when later steps run."""
+    g = load_golden("traj_small_h32_n3000_c10")
+    preds, labels = golden_slab(g)
+    sel = _mk(preds, labels)
+    kept = []
+    for k in range(int(g["steps"])):
+        gi = int(g["idx"][k])
+        sel.add_label(gi, int(labels[gi]), 0.0)
+        kept.append(sel.get_best_model_prediction())
+    assert [int(b) for b in kept] == [int(x) for x in g["best_model"]]
+    assert len({b.data_ptr() for b in kept}) == len(kept)

@@ -55,6 +55,8 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--dense", action="store_true", help="worst-case synthetic slab (wrong class uniform)")
+    ap.add_argument("--no-dense-extra", dest="dense_extra", action="store_false",
+                    help="skip the dense worst-case slab that the N=1 run reports under modes.dense_slab")
     return ap.parse_args()
 
 
@@ -270,6 +272,29 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------------
+HOT = {   # C-ABI entry point -> kernel name printed in the roofline line
+    "coda_b200_gain_eig": "k_gain_eig", "coda_b200_pi_rank1": "k_pi_rank1", "coda_b200_pair_rows_tc": "k_pair_rows_tc",
+    "coda_b200_pair_rows": "k_pair_rows", "coda_b200_pi_full": "k_pi_full", "coda_b200_template_gains": "k_template_gains",
+    "coda_b200_beta_tables": "k_beta_nodes+k_beta_combine+k_pb_normalize", "coda_b200_step_select": "k_step_select",
+    "coda_b200_step_mixture": "k_step_mixture",
+}
+
+
+def algorithmic_bytes(eng):
+    """Algorithmic bytes per launch, per shard."""
+    H, N, C, Hp = eng.H, eng.N, eng.C, eng.Hp
+    ent, heavy = eng.n_entries, eng.n_heavy
+    return {
+        # cached rows of the heavy pairs + U rows + entry lists + offsets + template-gain lookups; writes eig
+        "coda_b200_gain_eig": (4 * heavy * Hp if eng.ph_cache is not None else 4 * heavy) + 4 * N * C + 6 * ent + 8 * N
+                              + 4 * (ent - heavy) + 2 * N + 4 * N,
+        # one float per (model, item) + the U row pass (read all, write one column) + the ensemble column
+        "coda_b200_pi_rank1": 4 * H * N + 4 * N * C + 4 * N + 4 * N,
+        "coda_b200_pi_full": 4 * H * N * C + 4 * N * C,
+        "coda_b200_template_gains": 4 * eng.T * Hp + 4 * eng.T,
+    }
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -303,26 +328,15 @@ def main():
         comm = LocalComm()
     wl = WORKLOADS[args.workload]
     H, N, C = wl["H"], wl["N"], wl["C"]
+    if args.steps + args.warmup + 64 >= N:
+        raise SystemExit("bench: steps + warmup must stay below the number of items")
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     hbm_peak, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
-
-    t0 = time.time()
-    ds = SyntheticDataset(H, N, C, seed=args.seed, device=dev, dense=args.dense, rank=rank, world=world)
-    torch.cuda.synchronize()
-    t_gen = time.time() - t0
-    labels_dev = ds.labels.to(dev)
-    labels_host = ds.labels_host.numpy()
-
-    def make(mode):
-        random.seed(0)
-        t = time.time()
-        s = CODA(ds, mode=mode, comm=comm)
-        torch.cuda.synchronize()
-        return s, time.time() - t
+    tf_peak = peaks.get("bf16_tflops_sustained", 1400.0)
 
     def barrier():
         if world > 1:
@@ -336,28 +350,47 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    def device_loop(sel, warm, steps, profile_only=None):
+    def dataset(dense):
+        t = time.time()
+        ds = SyntheticDataset(H, N, C, seed=args.seed, device=dev, dense=dense, rank=rank, world=world)
+        torch.cuda.synchronize()
+        return ds, ds.labels.to(dev), ds.labels_host.numpy(), time.time() - t
+
+    def make(ds, mode):
+        random.seed(0)
+        t = time.time()
+        s = CODA(ds, mode=mode, comm=comm)
+        torch.cuda.synchronize()
+        return s, time.time() - t
+
+    def graph_loop(sel, labels_dev, warm, steps):
+        """`value`: host-free loop, one CUDA-graph replay per step, exchanges inside the kernels."""
         eng = sel.engine
-        hist_idx = torch.zeros(warm + steps, dtype=torch.int64, device=dev)
-        hist_q = torch.zeros(warm + steps, dtype=torch.float32, device=dev)
-        for k in range(warm):
-            eng.device_step(labels_dev, k, hist_idx, hist_q)
+        sel.run_steps(max(warm, 2), labels_dev)            # warm-up (>= 2: the first step is eager, then the capture)
         barrier()
         launches0 = eng.counters["launches"]
-        if profile_only is not None:
-            eng.start_profile(profile_only or None)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for k in range(warm, warm + steps):
-            eng.device_step(labels_dev, k, hist_idx, hist_q)
+        sel.run_steps(steps, labels_dev)
         e1.record()
         barrier()
         ms = max_over_ranks(e0.elapsed_time(e1))
-        prof = eng.stop_profile() if profile_only is not None else {}
         eng.check_flags(sync=True)
-        return ms, eng.counters["launches"] - launches0, prof, hist_idx.cpu().tolist()
+        return ms, eng.counters["launches"] - launches0
 
-    def api_loop(sel, warm, steps):
+    def eager_profile(sel, labels_dev, steps):
+        """Per-kernel CUDA-event times over a few eager steps (same kernels, launched one by one; not part of `value`)."""
+        eng = sel.engine
+        eng.loop_prepare(labels_dev)
+        barrier()
+        eng.start_profile()
+        for _ in range(steps):
+            eng.loop_eager()
+        prof = eng.stop_profile()
+        barrier()
+        return prof
+
+    def api_loop(sel, labels_host, warm, steps):
         """main.py:91-94 with a host oracle; every step copies {idx, class} H2D from pinned memory and reads
         the selection report + best model back."""
         best_host = torch.zeros(1, dtype=torch.int64).pin_memory()
@@ -385,20 +418,57 @@ def main():
         ms = max_over_ranks(max(e0.elapsed_time(e1), wall * 1e3))
         return ms, picks
 
+    def kernel_table(prof):
+        return {k.replace("coda_b200_", ""): {"avg_ms": v[1] / max(1, v[0]), "max_ms": v[2], "launches_per_step": v[0] / max(1, prof_steps)}
+                for k, v in prof.items()}
+
+    def roofline(eng, prof, ms_step, mode):
+        if not prof:
+            return None
+        dom = max(prof, key=lambda k: prof[k][1])
+        cnt, tot, mx = prof[dom]
+        avg_ms = tot / max(1, cnt)
+        alg = algorithmic_bytes(eng)
+        base = {"kernel": HOT.get(dom, dom), "avg_launch_ms": avg_ms, "share_of_step": (tot / prof_steps) / ms_step,
+                "peak_source": peak_src, "traffic": None}
+        if dom in alg:
+            ach = alg[dom] / (avg_ms * 1e-3) / 1e9
+            base.update(bound="hbm", achieved=ach, peak=hbm_peak, unit="GB/s", frac=ach / hbm_peak,
+                        algorithmic_bytes_per_launch=alg[dom])
+        elif dom == "coda_b200_pair_rows_tc":
+            # 9 bf16 MMAs of 128 x 256 x Hp (3 dL limbs) / 128 x Hp x 256 (2 tables x 3 cross terms) per 128-row tile
+            tiles = eng.ntiles if mode != "incremental" else max(1, eng.ntiles // C)
+            flops = 9 * 2 * 128 * 256 * eng.Hp * tiles
+            ach = flops / (avg_ms * 1e-3) / 1e12
+            base.update(bound="tensor", achieved=ach, peak=tf_peak, unit="TFLOP/s", frac=ach / tf_peak,
+                        algorithmic_flops_per_launch=flops)
+        else:
+            base.update(bound="hbm", achieved=None, peak=hbm_peak, unit="GB/s", frac=None)
+        try:    # measured DRAM traffic of the same kernel/config from the committed ncu capture (not measurable live)
+            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r2.json")))
+            ent = tr.get(f"{args.workload}/{world}/{mode}", {}).get(base["kernel"])
+            if ent:
+                base["traffic"], base["traffic_source"] = ent, "profiles/r2_step_kernels_ncu.txt"
+        except Exception:
+            pass
+        return base
+
     # ---- our arm -------------------------------------------------------------------------------------
-    sel, t_init = make(args.mode)
+    ds, labels_dev, labels_host, t_gen = dataset(args.dense)
+    sel, t_init = make(ds, args.mode)
     eng = sel.engine
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    hot = ["coda_b200_pi_rank1", "coda_b200_pair_gain", "coda_b200_pair_rows", "coda_b200_pair_rows_tc",
-           "coda_b200_eig_points", "coda_b200_pi_full"]
-    ms, launches, prof, picks_dev = device_loop(sel, args.warmup, args.steps, profile_only=hot)
+    ms, launches = graph_loop(sel, labels_dev, args.warmup, args.steps)
     value = args.steps / (ms / 1e3)
+    picks_dev = sel.history()[0][-(args.steps):].tolist()
+    ties_dev = int(sel.history()[2].sum())
 
-    # per-kernel shares over a few fully instrumented steps (not part of `value`)
-    _, _, prof_all, _ = device_loop(sel, 0, min(20, args.steps), profile_only=[])
+    prof_steps = min(10, args.steps)
+    prof = eager_profile(sel, labels_dev, prof_steps)
+    roof = roofline(eng, prof, ms / args.steps, args.mode)
 
     e2e_steps = args.e2e_steps or min(args.steps, 200)
-    ms_e2e, picks_api = api_loop(sel, max(1, min(args.warmup, 3)), e2e_steps)
+    ms_e2e, picks_api = api_loop(sel, labels_host, max(3, min(args.warmup, 5)), e2e_steps)
     # the clock sampler has been running since before the warm-up; a very short run may end before nvidia-smi has
     # produced samples, so keep the same load on (untimed) until a few exist
     t_wait = time.time()
@@ -406,66 +476,48 @@ def main():
         more = torch.tensor([1 if (sampler is not None and sampler.count() < 5 and time.time() - t_wait < 3.0) else 0],
                             device=dev)
         if world > 1:
-            dist.broadcast(more, src=0)        # every rank runs the same number of (collective) extra steps
+            dist.broadcast(more, src=0)        # every rank runs the same number of extra steps
         if not int(more.item()):
             break
-        device_loop(sel, 0, 20)
+        sel.run_steps(20, labels_dev)
+        torch.cuda.synchronize()
     clocks = sampler.stop() if sampler else {}
     e2e = e2e_steps / (ms_e2e / 1e3)
-    h2d = eng.sel_host.numel() * 8
-    d2h = eng.rep_host.numel() * 8 * (world if world > 1 else 1) + 8
+    h2d = 16
+    d2h = eng.rep_host.numel() * 8 + 8
+    info = dict(pairs=eng.npairs, heavy=eng.n_heavy, ent=eng.n_entries, n_loc=eng.N, shadow=eng.n_shadow,
+                tc=bool(eng.use_tc), mode=eng.mode)
+    kernels = kernel_table(prof)
 
     extra = {}
-    for m in [x for x in args.extra_modes.split(",") if x and x != args.mode]:
+    extra_list = [x for x in args.extra_modes.split(",") if x and x != args.mode]
+    for m in extra_list:                                        # other modes on the same slab, a few steps each
+        sel.close()
         del sel, eng
         torch.cuda.empty_cache()
-        sel, t_i = make(m)
+        sel, t_i = make(ds, m)
         eng = sel.engine
-        ms_m, _, prof_m, _ = device_loop(sel, 2, args.extra_steps, profile_only=hot)
+        ms_m, _ = graph_loop(sel, labels_dev, 2, args.extra_steps)
+        prof_steps = min(3, args.extra_steps)
+        pm = eager_profile(sel, labels_dev, prof_steps)
         extra[m] = {"value": args.extra_steps / (ms_m / 1e3), "unit": "steps/s", "ms_per_step": ms_m / args.extra_steps,
-                    "init_s": t_i, "kernel_ms": {k.replace("coda_b200_", ""): v[1] / max(1, v[0]) for k, v in prof_m.items()}}
-
-    # ---- roofline of the dominant kernel of the timed region -----------------------------------------
-    n_loc = eng.N
-    npairs, Hp = eng.npairs, eng.Hp
-    alg_bytes = {   # algorithmic bytes per launch, per rank
-        "coda_b200_pi_rank1": 4 * H * n_loc + 4 * n_loc * C + 4 * n_loc,
-        "coda_b200_pair_gain": 4 * npairs * Hp + 4 * npairs,
-        "coda_b200_eig_points": 4 * n_loc * C + 4 * n_loc + 6 * eng.n_entries,
-        "coda_b200_pi_full": 4 * H * n_loc * C + 4 * n_loc * C,
-    }
-    roof = None
-    if prof:
-        dom = max(prof, key=lambda k: prof[k][1])
-        cnt, tot = prof[dom]
-        avg_ms = tot / max(1, cnt)
-        if dom in alg_bytes:
-            ach = alg_bytes[dom] / (avg_ms * 1e-3) / 1e9
-            roof = {"kernel": dom.replace("coda_b200_", "k_"), "bound": "hbm", "achieved": ach, "peak": hbm_peak,
-                    "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
-                    "avg_launch_ms": avg_ms, "algorithmic_bytes_per_launch": alg_bytes[dom],
-                    "share_of_step": tot / ms}
-        elif dom == "coda_b200_pair_rows_tc":
-            # 9 bf16 MMAs of 128 x 256 x Hp (3 dL limbs) / 128 x Hp x 256 (2 tables x 3 cross terms) per 128-pair tile
-            tiles_per_launch = eng.ntiles if args.mode != "incremental" else max(1, eng.ntiles // C)
-            flops = 9 * 2 * 128 * 256 * eng.Hp * tiles_per_launch
-            tf_peak = peaks.get("bf16_tflops_sustained", 1400.0)
-            ach = flops / (avg_ms * 1e-3) / 1e12
-            roof = {"kernel": "k_pair_rows_tc", "bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s",
-                    "frac": ach / tf_peak, "traffic": None, "peak_source": peak_src, "avg_launch_ms": avg_ms,
-                    "algorithmic_flops_per_launch": flops, "share_of_step": tot / ms}
-        else:
-            roof = {"kernel": dom.replace("coda_b200_", "k_"), "bound": "hbm", "avg_launch_ms": avg_ms,
-                    "share_of_step": tot / ms, "achieved": None, "peak": hbm_peak, "unit": "GB/s", "frac": None,
-                    "traffic": None}
-
-    if roof is not None:
-        try:    # measured DRAM traffic of the same kernel/config from the committed ncu capture (not measurable live)
-            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")))
-            roof["traffic"] = tr.get(f"{args.workload}/{world}/{args.mode}", {}).get(roof["kernel"])
-            roof["traffic_source"] = "profiles/r1_step_kernels_ncu.txt" if roof["traffic"] else None
-        except Exception:
-            pass
+                    "init_s": t_i, "roofline": roofline(eng, pm, ms_m / args.extra_steps, m), "kernel_ms": kernel_table(pm)}
+    if args.dense_extra and not args.dense and world == 1:
+        # the dense worst case (wrong class uniform over all C) beside the default slab
+        sel.close()
+        del sel, eng, ds
+        torch.cuda.empty_cache()
+        ds2, lab2, _lh2, _ = dataset(True)
+        sel, t_i = make(ds2, args.mode)
+        eng = sel.engine
+        ms_d, _ = graph_loop(sel, lab2, 3, args.extra_steps * 2)
+        prof_steps = min(3, args.extra_steps)
+        pd = eager_profile(sel, lab2, prof_steps)
+        extra["dense_slab"] = {"value": args.extra_steps * 2 / (ms_d / 1e3), "unit": "steps/s", "mode": eng.mode,
+                               "ms_per_step": ms_d / (args.extra_steps * 2), "init_s": t_i,
+                               "nnz_frac": eng.n_entries / max(1, eng.N) / C, "heavy_rows": eng.n_heavy,
+                               "roofline": roofline(eng, pd, ms_d / (args.extra_steps * 2), eng.mode),
+                               "kernel_ms": kernel_table(pd)}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:      # rank 0, N=1 only (the reference arm covers N>1)
         cpu = cpu_baseline(wl, args.cpu_seconds, args.seed, args.dense)
@@ -477,17 +529,20 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {
                 "workload": workload_string(args, wl, world),
-                "mode": args.mode, "l2": "per-step working set (slab gather + row cache + U) >> 126 MB L2; no flush needed",
-                "tie_rule_value": "arg-max, first index (device loop)", "tie_rule_e2e": "random.choice (coda.py:308)",
-                "pairs": npairs, "heavy_pairs": eng.n_heavy, "tensor_core_rows": bool(eng.use_tc), "entries_per_item": eng.n_entries / max(1, n_loc),
-                "gen_s": t_gen, "init_s": t_init, "shadow_models": eng.n_shadow,
+                "mode": info["mode"], "l2": "per-step working set (row cache + U + slab gather) >> 126 MB L2; no flush needed",
+                "loop": "CUDA graph, one replay per step; shards exchange through peer memory inside the step kernels",
+                "tie_rule_value": "arg-max, first index (device loop); isclose ties in the timed run: %d" % ties_dev,
+                "tie_rule_e2e": "random.choice (coda.py:308)",
+                "rows": info["pairs"], "heavy_rows": info["heavy"], "tensor_core_rows": info["tc"],
+                "entries_per_item": info["ent"] / max(1, info["n_loc"]), "nnz_frac": info["ent"] / max(1, info["n_loc"]) / C,
+                "gen_s": t_gen, "init_s": t_init, "shadow_models": info["shadow"],
             },
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": "steps/s", "ms_per_step": ms_e2e / e2e_steps, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps},
             "gpu_launches": launches,
             "roofline": roof,
-            "kernel_ms": {k.replace("coda_b200_", ""): v[1] / max(1, v[0]) for k, v in prof_all.items()},
+            "kernel_ms": kernels,
             "modes": extra,
             "cpu_baseline": cpu,
             "first_picks": {"device_loop": picks_dev[:8], "api": [p[0] for p in picks_api[:8]]},

@@ -11,7 +11,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libcoda_b200.so")
-SOURCES = ["api.cu", "slab.cu", "tables.cu", "pairs.cu", "pairs_tc.cu", "select.cu"]
+SOURCES = ["api.cu", "xchg.cu", "slab.cu", "tables.cu", "pairs.cu", "pairs_tc.cu", "gain.cu", "step.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",
@@ -35,6 +35,11 @@ def _digest() -> str:
 
 def _fresh(stamp, dig):
     return os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read().strip() == dig
+
+
+def is_fresh() -> bool:
+    """True when the in-tree library was built from exactly the current csrc/ + include/ + flags."""
+    return _fresh(os.path.join(LIBDIR, "build.sha256"), _digest())
 
 
 def build(force: bool = False, verbose: bool = False) -> str:

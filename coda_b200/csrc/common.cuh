@@ -115,24 +115,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
-// bounded variant for pipelines under development: traps (context error, no hang) after ~2^24 polls
-__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
-  uint32_t done = 0;
-  for (uint32_t it = 0; it < (1u << 24); ++it) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}"
-        : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    if (done) return;
-  }
-  printf("coda_b200: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-  __trap();
-}
 // global -> shared bulk copy; bytes % 16 == 0, both addresses 16-byte aligned.
 __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
   asm volatile(
@@ -140,4 +122,64 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
           smem_u32(smem_dst)),
       "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
+}
+
+// ---- arg-max records ---------------------------------------------------------------------------
+// One record = CODA_B200_REC_WORDS int64: {bits(vA), iA, cntA, bits(vB), iB, bits(v2A), bits(v2B), 0}.
+//   set A = unlabeled & non-unanimous items (coda.py:215-219), set B = all unlabeled items (coda.py:239 fallback);
+//   v / i = best value and its lowest global index (torch.argmax: first maximum, coda.py:309), cnt = |A|,
+//   v2 = best value among the OTHER items of the set (for the isclose tie test of coda.py:307).
+#define IDX_NONE 0x7fffffffffffffffLL
+#define REC_W CODA_B200_REC_WORDS
+
+struct Best2 {
+  float v;
+  long long i;
+  float v2;
+};
+__device__ __forceinline__ Best2 best2_empty() { return Best2{-INFINITY, IDX_NONE, -INFINITY}; }
+__device__ __forceinline__ void best2_add(Best2& b, float v, long long i) {
+  if (v > b.v || (v == b.v && i < b.i)) {
+    b.v2 = fmaxf(b.v2, b.v);
+    b.v = v;
+    b.i = i;
+  } else {
+    b.v2 = fmaxf(b.v2, v);
+  }
+}
+__device__ __forceinline__ void best2_merge(Best2& b, const Best2& o) {
+  if (o.i == IDX_NONE) return;
+  if (b.i == IDX_NONE) { b = o; return; }
+  if (o.v > b.v || (o.v == b.v && o.i < b.i)) {
+    const float lose = b.v;
+    b.v2 = fmaxf(fmaxf(b.v2, o.v2), lose);
+    b.v = o.v;
+    b.i = o.i;
+  } else {
+    b.v2 = fmaxf(fmaxf(b.v2, o.v2), o.v);
+  }
+}
+__device__ __forceinline__ void best2_warp(Best2& b) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    Best2 t;
+    t.v = __shfl_xor_sync(CODA_FULL, b.v, o);
+    t.i = __shfl_xor_sync(CODA_FULL, b.i, o);
+    t.v2 = __shfl_xor_sync(CODA_FULL, b.v2, o);
+    best2_merge(b, t);
+  }
+}
+__device__ __forceinline__ void rec_store(long long* out, const Best2& a, long long cntA, const Best2& b) {
+  out[0] = (long long)__float_as_int(a.v); out[1] = a.i; out[2] = cntA;
+  out[3] = (long long)__float_as_int(b.v); out[4] = b.i;
+  out[5] = (long long)__float_as_int(a.v2); out[6] = (long long)__float_as_int(b.v2); out[7] = 0;
+}
+__device__ __forceinline__ void rec_load(const long long* r, Best2& a, long long& cntA, Best2& b) {
+  a.v = __int_as_float((int)r[0]); a.i = r[1]; cntA = r[2];
+  b.v = __int_as_float((int)r[3]); b.i = r[4];
+  a.v2 = __int_as_float((int)r[5]); b.v2 = __int_as_float((int)r[6]);
+}
+// torch.isclose(q, best, rtol=1e-8) with the default atol=1e-8, evaluated in fp32 (coda.py:307)
+__device__ __forceinline__ bool isclose_best(float q, float best) {
+  return q == best || fabsf(q - best) <= 1e-8f + fabsf(1e-8f * best);
 }

@@ -30,7 +30,8 @@ constexpr int STAGES_B = 3;
 
 struct TcArgs {
   const int4* tiles;             // (class, first pid, count <= 128, unused)
-  const uint32_t* zmask;         // [npairs][W]
+  const uint32_t* zmask;         // [npairs][W]   (work-list order)
+  const int32_t* row_of;         // [npairs]      work-list position -> row id
   const __nv_bfloat16* dLb;      // [C][Hp/KA][3][TC_NODES x KA]      core-matrix order, rows = nodes
   const __nv_bfloat16* Gb;       // [C][TC_NODES/KB][4][Hp x KB]      core-matrix order, rows = models
   const float* PB;               // [C][Hp]
@@ -201,11 +202,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_pair_rows_tc(TcArgs a, int ti
       const int kn = kc + STAGES_A - 1;
       if (kn < nka) {
         const int s1 = kn % STAGES_A;
-        if (kn >= STAGES_A) mbar_wait_bounded(&emptyA[s1], ((kn / STAGES_A) - 1) & 1);
+        if (kn >= STAGES_A) mbar_wait(&emptyA[s1], ((kn / STAGES_A) - 1) & 1);
         mbar_expect_tx(&fullA[s1], bytesA);
         tma_load_1d(stgA + (size_t)s1 * 48 * 1024, src + (size_t)kn * bytesA, bytesA, &fullA[s1]);
       }
-      mbar_wait_bounded(&fullA[s], (kc / STAGES_A) & 1);
+      mbar_wait(&fullA[s], (kc / STAGES_A) & 1);
       tc_fence_after();
 #pragma unroll
       for (int limb = 0; limb < 3; ++limb) {
@@ -225,7 +226,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_pair_rows_tc(TcArgs a, int ti
     mma_commit(doneA);
     // prefetch the first phase-B stages while the epilogue below runs (their smem region is free once the
     // phase-A MMAs have completed, which doneA certifies)
-    mbar_wait_bounded(doneA, 0);
+    mbar_wait(doneA, 0);
     const unsigned char* srcB = reinterpret_cast<const unsigned char*>(a.Gb) + (size_t)c * nkb * bytesB;
     for (int kc = 0; kc < STAGES_B - 1 && kc < nkb; ++kc) {
       mbar_expect_tx(&fullB[kc], bytesB);
@@ -233,7 +234,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_pair_rows_tc(TcArgs a, int ti
     }
   }
   __syncwarp();
-  mbar_wait_bounded(doneA, 0);
+  mbar_wait(doneA, 0);
   tc_fence_after();
 
   // ---- epilogue A: D = exp(logD) -> bf16 hi / lo limbs in the A-operand layout ---------------------
@@ -276,11 +277,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_pair_rows_tc(TcArgs a, int ti
       const int kn = kc + STAGES_B - 1;          // chunk to prefetch now
       if (kn < nkb) {
         const int sn = kn % STAGES_B;
-        if (kn >= STAGES_B) mbar_wait_bounded(&emptyB[sn], ((kn / STAGES_B) - 1) & 1);
+        if (kn >= STAGES_B) mbar_wait(&emptyB[sn], ((kn / STAGES_B) - 1) & 1);
         mbar_expect_tx(&fullB[sn], bytesB);
         tma_load_1d(stg + (size_t)sn * 32 * 1024, srcB + (size_t)kn * bytesB, bytesB, &fullB[sn]);
       }
-      mbar_wait_bounded(&fullB[s], (kc / STAGES_B) & 1);
+      mbar_wait(&fullB[s], (kc / STAGES_B) & 1);
       tc_fence_after();
       const uint64_t ahi = smem_desc(opA_s + (uint32_t)(kc * 2) * (TC_M / 8) * 128, (TC_M / 8) * 128, 128);
       const uint64_t alo = smem_desc(opA_s + 64 * 1024 + (uint32_t)(kc * 2) * (TC_M / 8) * 128, (TC_M / 8) * 128, 128);
@@ -299,7 +300,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_pair_rows_tc(TcArgs a, int ti
     mma_commit(doneB);
   }
   __syncwarp();
-  mbar_wait_bounded(doneB, 0);
+  mbar_wait(doneB, 0);
   tc_fence_after();
 
   // ---- epilogue B: (pair, column half) per thread ---------------------------------------------------
@@ -327,7 +328,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_pair_rows_tc(TcArgs a, int ti
     const float rden = 1.0f / fmaxf(sum, 1e-30f);                    // coda.py:114
     const float pic = want_gain ? a.pi_hat[c] : 0.f;
     float g = 0.f;
-    float* cache = (a.ph_cache && row < cnt) ? a.ph_cache + (size_t)(pid0 + row) * Hp : nullptr;
+    const int orow = row < cnt ? a.row_of[pid0 + row] : 0;
+    if (row < cnt && half == 0 && sum < 0.9999e-30f) bad |= CODA_B200_FLAG_ROWSUM_WARN;    // util.py:37-39
+    float* cache = (a.ph_cache && row < cnt) ? a.ph_cache + (size_t)orow * Hp : nullptr;
 #pragma unroll
     for (int ch = 0; ch < 8; ++ch) {
       if (ch < ch_lo || ch >= ch_hi) continue;
@@ -340,6 +343,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_pair_rows_tc(TcArgs a, int ti
         const int h = ch * 32 + i;
         float ph = (((zb >> i) & 1u) ? p1[i] : p0[i]) * rden;
         if (h >= H) ph = 0.f;
+        if (ph < -1e-12f) bad |= CODA_B200_FLAG_NEGATIVE_PROB;          // util.py:33-35
         p0[i] = ph;
         if (want_gain && h < H) {
           const float m = m0s[h];
@@ -355,7 +359,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_pair_rows_tc(TcArgs a, int ti
     if (want_gain) {
       xgain[half * TC_M + row] = g;
       __syncthreads();
-      if (half == 0 && row < cnt) a.gain[pid0 + row] = xgain[row] + xgain[TC_M + row];
+      if (half == 0 && row < cnt) a.gain[orow] = xgain[row] + xgain[TC_M + row];
     }
     if (bad) atomicOr(a.flags, bad);
   }
@@ -369,10 +373,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_pair_rows_tc(TcArgs a, int ti
 }  // namespace
 
 extern "C" int coda_b200_pair_rows_tc(const int32_t* tiles128, int tile_lo, int tile_hi, const uint32_t* zmask,
-                                      const void* dLb, const void* Gb, const float* PB, const float* m0,
+                                      const int32_t* row_of, const void* dLb, const void* Gb, const float* PB, const float* m0,
                                       const float* pi_hat, int H, float* ph_cache, float* gain, const int64_t* sel,
                                       const int64_t* tile_off, uint32_t* flags, coda_stream_t stream) {
-  CODA_CHECK_ARG(tiles128 && zmask && dLb && Gb && PB && flags, "pair_rows_tc: null pointer");
+  CODA_CHECK_ARG(tiles128 && zmask && row_of && dLb && Gb && PB && flags, "pair_rows_tc: null pointer");
   CODA_CHECK_ARG((gain && m0 && pi_hat) || (!gain && ph_cache), "pair_rows_tc: need gain (+m0, pi_hat) or ph_cache");
   CODA_CHECK_ARG(!sel || tile_off, "pair_rows_tc: sel needs tile_off");
   const int Hp = (H + 31) / 32 * 32;
@@ -381,6 +385,7 @@ extern "C" int coda_b200_pair_rows_tc(const int32_t* tiles128, int tile_lo, int 
   TcArgs a;
   a.tiles = reinterpret_cast<const int4*>(tiles128);
   a.zmask = zmask;
+  a.row_of = row_of;
   a.dLb = reinterpret_cast<const __nv_bfloat16*>(dLb);
   a.Gb = reinterpret_cast<const __nv_bfloat16*>(Gb);
   a.PB = PB; a.m0 = m0; a.pi_hat = pi_hat; a.ph_cache = ph_cache; a.gain = gain; a.flags = flags;

@@ -10,11 +10,12 @@
 //   label_row / label_apply / pi_rank1   coda.py:316-319 (posterior update + marginal refresh,
 //                      restated as the rank-1 column update it algebraically is)
 #include "common.cuh"
+#include "terms.cuh"
 
 // ---------------------------------------------------------------------------------------
 // scan_slab: one pass over the slab.  CTA = tile of TN points, all H models.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_scan_slab(const float* __restrict__ preds, int H, long long N, int C,
+__global__ void __launch_bounds__(256) k_scan_slab(const float* __restrict__ preds, long long ldh, int H, long long N, int C,
                                                    int TN, uint16_t* __restrict__ hard,
                                                    int32_t* __restrict__ pseudo, uint8_t* __restrict__ disagree,
                                                    float* __restrict__ ens_out, uint32_t* __restrict__ flags) {
@@ -28,7 +29,7 @@ __global__ void __launch_bounds__(256) k_scan_slab(const float* __restrict__ pre
   __syncthreads();
   uint32_t bad = 0;
   for (int h = 0; h < H; ++h) {
-    const float* base = preds + ((size_t)h * N + n0) * C;
+    const float* base = preds + (size_t)h * ldh + (size_t)n0 * C;
     for (int p = warp; p < tn; p += nwarp) {
       const float* row = base + (size_t)p * C;
       float* erow = ens + (size_t)p * C;
@@ -85,7 +86,7 @@ __global__ void __launch_bounds__(256) k_scan_slab(const float* __restrict__ pre
 #define SS_TN 32
 #define SS_ST 4
 template <int KC>
-__global__ void __launch_bounds__(256) k_scan_slab_tma(const float* __restrict__ preds, int H, long long N, int C,
+__global__ void __launch_bounds__(256) k_scan_slab_tma(const float* __restrict__ preds, long long ldh, int H, long long N, int C,
                                                        uint16_t* __restrict__ hard, int32_t* __restrict__ pseudo,
                                                        uint8_t* __restrict__ disagree, float* __restrict__ ens_out,
                                                        uint32_t* __restrict__ flags) {
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(256) k_scan_slab_tma(const float* __restrict__
   if (threadIdx.x == 0) {
     for (int s = 0; s < SS_ST && s < H; ++s) {
       mbar_expect_tx(&full[s], bytes);
-      tma_load_1d(reinterpret_cast<unsigned char*>(bufs) + s * buf_bytes, preds + ((size_t)s * N + n0) * C, bytes, &full[s]);
+      tma_load_1d(reinterpret_cast<unsigned char*>(bufs) + s * buf_bytes, preds + (size_t)s * ldh + (size_t)n0 * C, bytes, &full[s]);
     }
   }
   float ens[4][KC];
@@ -160,7 +161,7 @@ __global__ void __launch_bounds__(256) k_scan_slab_tma(const float* __restrict__
     __syncthreads();                                   // everyone is done with buf[s]
     if (threadIdx.x == 0 && h + SS_ST < H) {
       mbar_expect_tx(&full[s], bytes);
-      tma_load_1d(reinterpret_cast<unsigned char*>(bufs) + s * buf_bytes, preds + ((size_t)(h + SS_ST) * N + n0) * C, bytes,
+      tma_load_1d(reinterpret_cast<unsigned char*>(bufs) + s * buf_bytes, preds + (size_t)(h + SS_ST) * ldh + (size_t)n0 * C, bytes,
                   &full[s]);
     }
   }
@@ -198,11 +199,14 @@ __global__ void __launch_bounds__(256) k_scan_slab_tma(const float* __restrict__
   if (bad) atomicOr(flags, bad);
 }
 
-extern "C" int coda_b200_scan_slab(const float* preds, int H, int64_t N, int C, uint16_t* hard, int32_t* pseudo,
-                                   uint8_t* disagree, float* ens_out, uint32_t* flags, coda_stream_t stream) {
+extern "C" int coda_b200_scan_slab(const float* preds, int64_t model_stride, int H, int64_t N, int C, uint16_t* hard,
+                                   int32_t* pseudo, uint8_t* disagree, float* ens_out, uint32_t* flags,
+                                   coda_stream_t stream) {
   CODA_CHECK_ARG(preds && hard && pseudo && disagree && flags, "scan_slab: null pointer");
+  CODA_CHECK_ARG(model_stride >= (int64_t)N * C, "scan_slab: model_stride %lld < N*C", (long long)model_stride);
+  const long long ldh = model_stride;
   CODA_CHECK_ARG(H >= 1 && C >= 2 && C <= 65535 && N >= 1, "scan_slab: bad dims H=%d N=%lld C=%d", H, (long long)N, C);
-  if (C <= 128 && ((long long)N * C) % 4 == 0 && ((N % SS_TN) * C) % 4 == 0 &&
+  if (C <= 128 && ldh % 4 == 0 && ((long long)SS_TN * C) % 4 == 0 && ((N % SS_TN) * C) % 4 == 0 &&
       (reinterpret_cast<uintptr_t>(preds) & 15) == 0) {
     const size_t buf_bytes = ((size_t)SS_TN * C * 4 + 127) / 128 * 128;
     const size_t smem = SS_ST * buf_bytes + (((size_t)SS_TN * H * 2 + 15) / 16) * 16 + SS_ST * 8;
@@ -212,7 +216,7 @@ extern "C" int coda_b200_scan_slab(const float* preds, int H, int64_t N, int C, 
 #define LAUNCH_SS(KC)                                                                                             \
   do {                                                                                                            \
     CODA_CUDA_OK(cudaFuncSetAttribute(k_scan_slab_tma<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    k_scan_slab_tma<KC><<<(unsigned)grid, 256, smem, st>>>(preds, H, N, C, hard, pseudo, disagree, ens_out, flags);  \
+    k_scan_slab_tma<KC><<<(unsigned)grid, 256, smem, st>>>(preds, ldh, H, N, C, hard, pseudo, disagree, ens_out, flags); \
   } while (0)
       if (C <= 32) LAUNCH_SS(1);
       else if (C <= 64) LAUNCH_SS(2);
@@ -233,7 +237,7 @@ extern "C" int coda_b200_scan_slab(const float* preds, int H, int64_t N, int C, 
   CODA_CHECK_ARG(need <= 200 * 1024, "scan_slab: H=%d C=%d does not fit shared memory", H, C);
   CODA_CUDA_OK(cudaFuncSetAttribute(k_scan_slab, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
   long long grid = (N + TN - 1) / TN;
-  k_scan_slab<<<(unsigned)grid, 256, need, as_stream(stream)>>>(preds, H, N, C, TN, hard, pseudo, disagree, ens_out, flags);
+  k_scan_slab<<<(unsigned)grid, 256, need, as_stream(stream)>>>(preds, ldh, H, N, C, TN, hard, pseudo, disagree, ens_out, flags);
   CODA_LAUNCH_OK("k_scan_slab");
   return CODA_B200_OK;
 }
@@ -243,7 +247,7 @@ extern "C" int coda_b200_scan_slab(const float* preds, int H, int64_t N, int C, 
 // result does not depend on summation order or on how N is sharded across GPUs.
 // grid = (chunks, H).  Shared-memory table when C*C*8 fits, global atomics otherwise.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_confusion_accum(const float* __restrict__ preds,
+__global__ void __launch_bounds__(256) k_confusion_accum(const float* __restrict__ preds, long long ldh,
                                                          const int32_t* __restrict__ pseudo, int H, long long N,
                                                          int C, float fxs, long long chunk, int use_smem,
                                                          unsigned long long* __restrict__ conf_fx) {
@@ -261,7 +265,7 @@ __global__ void __launch_bounds__(256) k_confusion_accum(const float* __restrict
   unsigned long long* dst_tab = use_smem ? tab : gtab;
   for (long long n = n_lo + warp; n < n_hi; n += nwarp) {
     const int y = pseudo[n];
-    const float* row = preds + ((size_t)h * N + n) * C;
+    const float* row = preds + (size_t)h * ldh + (size_t)n * C;
     unsigned long long* dst = dst_tab + (size_t)y * C;
     for (int j = lane; j < C; j += 32) {
       long long v = to_fx(__ldg(row + j), fxs);
@@ -282,7 +286,7 @@ __global__ void __launch_bounds__(256) k_confusion_accum(const float* __restrict
 // handful of global atomics when the class changes -- no shared-memory atomics on the slab-sized stream.
 #define CS_RUN 256
 template <int KC>
-__global__ void __launch_bounds__(256) k_confusion_sorted(const float* __restrict__ preds,
+__global__ void __launch_bounds__(256) k_confusion_sorted(const float* __restrict__ preds, long long ldh,
                                                           const int32_t* __restrict__ pseudo,
                                                           const int32_t* __restrict__ order, int H, long long N, int C,
                                                           float fxs, unsigned long long* __restrict__ conf_fx) {
@@ -291,7 +295,7 @@ __global__ void __launch_bounds__(256) k_confusion_sorted(const float* __restric
   const long long i0 = ((long long)blockIdx.x * 8 + warp) * CS_RUN;
   const long long i1 = min(N, i0 + CS_RUN);
   if (i0 >= N) return;
-  const float* slab = preds + (size_t)h * N * C;
+  const float* slab = preds + (size_t)h * ldh;
   unsigned long long* tab = conf_fx + (size_t)h * C * C;
   long long acc[KC];
 #pragma unroll
@@ -338,8 +342,10 @@ __global__ void __launch_bounds__(256) k_confusion_sorted(const float* __restric
   flush();
 }
 
-extern "C" int coda_b200_confusion_sorted(const float* preds, const int32_t* pseudo, const int32_t* order, int H,
-                                          int64_t N, int C, int fx_shift, int64_t* conf_fx, coda_stream_t stream) {
+extern "C" int coda_b200_confusion_sorted(const float* preds, int64_t model_stride, const int32_t* pseudo,
+                                          const int32_t* order, int H, int64_t N, int C, int fx_shift,
+                                          int64_t* conf_fx, coda_stream_t stream) {
+  const long long ldh = model_stride;
   CODA_CHECK_ARG(preds && pseudo && order && conf_fx, "confusion_sorted: null pointer");
   CODA_CHECK_ARG(fx_shift >= 8 && fx_shift <= 46, "confusion_sorted: bad fx_shift %d", fx_shift);
   CODA_CHECK_ARG(C <= 128, "confusion_sorted: C=%d > 128 (use confusion_accum)", C);
@@ -348,16 +354,16 @@ extern "C" int coda_b200_confusion_sorted(const float* preds, const int32_t* pse
   const float fxs = exp2f((float)fx_shift);
   unsigned long long* out = reinterpret_cast<unsigned long long*>(conf_fx);
   cudaStream_t st = as_stream(stream);
-  if (C <= 32) k_confusion_sorted<1><<<grid, 256, 0, st>>>(preds, pseudo, order, H, N, C, fxs, out);
-  else if (C <= 64) k_confusion_sorted<2><<<grid, 256, 0, st>>>(preds, pseudo, order, H, N, C, fxs, out);
-  else if (C <= 96) k_confusion_sorted<3><<<grid, 256, 0, st>>>(preds, pseudo, order, H, N, C, fxs, out);
-  else k_confusion_sorted<4><<<grid, 256, 0, st>>>(preds, pseudo, order, H, N, C, fxs, out);
+  if (C <= 32) k_confusion_sorted<1><<<grid, 256, 0, st>>>(preds, ldh, pseudo, order, H, N, C, fxs, out);
+  else if (C <= 64) k_confusion_sorted<2><<<grid, 256, 0, st>>>(preds, ldh, pseudo, order, H, N, C, fxs, out);
+  else if (C <= 96) k_confusion_sorted<3><<<grid, 256, 0, st>>>(preds, ldh, pseudo, order, H, N, C, fxs, out);
+  else k_confusion_sorted<4><<<grid, 256, 0, st>>>(preds, ldh, pseudo, order, H, N, C, fxs, out);
   CODA_LAUNCH_OK("k_confusion_sorted");
   return CODA_B200_OK;
 }
 
-extern "C" int coda_b200_confusion_accum(const float* preds, const int32_t* pseudo, int H, int64_t N, int C,
-                                         int fx_shift, int64_t* conf_fx, coda_stream_t stream) {
+extern "C" int coda_b200_confusion_accum(const float* preds, int64_t model_stride, const int32_t* pseudo, int H,
+                                         int64_t N, int C, int fx_shift, int64_t* conf_fx, coda_stream_t stream) {
   CODA_CHECK_ARG(preds && pseudo && conf_fx, "confusion_accum: null pointer");
   CODA_CHECK_ARG(fx_shift >= 8 && fx_shift <= 46, "confusion_accum: bad fx_shift %d", fx_shift);
   size_t tab = (size_t)C * C * 8;
@@ -367,7 +373,7 @@ extern "C" int coda_b200_confusion_accum(const float* preds, const int32_t* pseu
   long long chunk = 8192;
   long long chunks = (N + chunk - 1) / chunk;
   dim3 grid((unsigned)chunks, (unsigned)H);
-  k_confusion_accum<<<grid, 256, smem, as_stream(stream)>>>(preds, pseudo, H, N, C, exp2f((float)fx_shift), chunk, use_smem,
+  k_confusion_accum<<<grid, 256, smem, as_stream(stream)>>>(preds, (long long)model_stride, pseudo, H, N, C, exp2f((float)fx_shift), chunk, use_smem,
                                                            reinterpret_cast<unsigned long long*>(conf_fx));
   CODA_LAUNCH_OK("k_confusion_accum");
   return CODA_B200_OK;
@@ -416,8 +422,9 @@ extern "C" int coda_b200_init_dirichlets(const int64_t* conf_fx, int H, int C, i
 #define PF_TN 64
 #define PF_TC 128
 #define PF_SK 32
-__global__ void __launch_bounds__(256) k_pi_full(const float* __restrict__ preds, const float* __restrict__ D,
-                                                 int H, long long N, int C, float* __restrict__ U) {
+__global__ void __launch_bounds__(256) k_pi_full(const float* __restrict__ preds, long long ldh,
+                                                 const float* __restrict__ D, int H, long long N, int C,
+                                                 float* __restrict__ U) {
   __shared__ float As[PF_TN][PF_SK + 1];
   __shared__ float Bs[PF_TC][PF_SK + 1];
   const int tid = threadIdx.x;
@@ -430,7 +437,7 @@ __global__ void __launch_bounds__(256) k_pi_full(const float* __restrict__ preds
 #pragma unroll
       for (int k = 0; k < 8; ++k) acc[i][k] = 0.f;
     for (int h = 0; h < H; ++h) {
-      const float* Ah = preds + ((size_t)h * N) * C;
+      const float* Ah = preds + (size_t)h * ldh;
       const float* Dh = D + ((size_t)h * C) * C;
       for (int s0 = 0; s0 < C; s0 += PF_SK) {
         __syncthreads();
@@ -473,11 +480,11 @@ __global__ void __launch_bounds__(256) k_pi_full(const float* __restrict__ preds
   }
 }
 
-extern "C" int coda_b200_pi_full(const float* preds, const float* D, int H, int64_t N, int C, float* U,
-                                 coda_stream_t stream) {
+extern "C" int coda_b200_pi_full(const float* preds, int64_t model_stride, const float* D, int H, int64_t N, int C,
+                                 float* U, coda_stream_t stream) {
   CODA_CHECK_ARG(preds && D && U, "pi_full: null pointer");
   long long grid = (N + PF_TN - 1) / PF_TN;
-  k_pi_full<<<(unsigned)grid, 256, 0, as_stream(stream)>>>(preds, D, H, N, C, U);
+  k_pi_full<<<(unsigned)grid, 256, 0, as_stream(stream)>>>(preds, (long long)model_stride, D, H, N, C, U);
   CODA_LAUNCH_OK("k_pi_full");
   return CODA_B200_OK;
 }
@@ -549,161 +556,48 @@ extern "C" int coda_b200_pi_reduce(float* U, int64_t N, int C, int fx_shift, flo
 // posterior update (coda.py:316-317) and the marginal refresh it triggers (coda.py:319),
 // restated:  D[h, t, j_h] += lr   with j_h = p_h(idx)   changes only row t of every D[h], so
 //   U[n, t] += lr * sum_h preds[h, n, j_h]      and every other column of U is untouched.
-// label_row   : owner of idx publishes j_h (jvec) and marks the point labeled
-// label_apply : every rank applies the increment to its replica of D
+// (the label itself -- owner's p_h(idx), labeled mark, D update, gather list -- is in step.cu)
 // pi_rank1    : gathers one float per (h, n) (one 32 B sector each), updates column t of U,
 //               renormalises rows on the fly and re-accumulates sum_n pi_hat_xi[n, :]
 // ---------------------------------------------------------------------------------------
-__global__ void k_label_row(const uint16_t* __restrict__ hard, int H, long long N, const long long* __restrict__ sel,
-                            int32_t* __restrict__ jvec, uint8_t* __restrict__ labeled) {
-  const long long idx = sel[0];
-  if (idx < 0 || idx >= N) {          // not owned by this shard: contribute zeros to the SUM all-reduce of jvec
-    for (int h = threadIdx.x; h < H; h += blockDim.x) jvec[h] = 0;
-    return;
-  }
-  for (int h = threadIdx.x; h < H; h += blockDim.x) jvec[h] = hard[(size_t)idx * H + h];
-  if (threadIdx.x == 0) labeled[idx] = 1;
-}
-
-__global__ void k_label_apply(float* __restrict__ D, int H, int C, const long long* __restrict__ sel,
-                              const int32_t* __restrict__ jvec, float lr) {
-  const int t = (int)sel[1];
-  if (t < 0 || t >= C) return;
-  for (int h = threadIdx.x; h < H; h += blockDim.x) {
-    int j = jvec[h];
-    D[((size_t)h * C + t) * C + j] += lr;                          // coda.py:317
-  }
-}
-
-extern "C" int coda_b200_label_row(const uint16_t* hard, int H, int64_t N, const int64_t* sel, int32_t* jvec,
-                                   uint8_t* labeled, coda_stream_t stream) {
-  CODA_CHECK_ARG(hard && sel && jvec && labeled, "label_row: null pointer");
-  k_label_row<<<1, 256, 0, as_stream(stream)>>>(hard, H, N, reinterpret_cast<const long long*>(sel), jvec, labeled);
-  CODA_LAUNCH_OK("k_label_row");
-  return CODA_B200_OK;
-}
-
-extern "C" int coda_b200_label_apply(float* D, int H, int C, const int64_t* sel, const int32_t* jvec, double lr,
-                                     coda_stream_t stream) {
-  CODA_CHECK_ARG(D && sel && jvec, "label_apply: null pointer");
-  k_label_apply<<<1, 256, 0, as_stream(stream)>>>(D, H, C, reinterpret_cast<const long long*>(sel), jvec, (float)lr);
-  CODA_LAUNCH_OK("k_label_apply");
-  return CODA_B200_OK;
-}
-
 // ---------------------------------------------------------------------------------------
 // class-major shadow copy  T[s][c][n] = preds[h_s][n][c]  for a subset of models (as many as spare HBM
 // allows, least accurate first).  The rank-1 refresh needs ONE float per (model, item): from the reference
 // layout that costs a 64-byte DRAM fetch each, from the shadow it is a coalesced 4-byte read.
 // grid = (ceil(N/32), ceil(C/32), S), block = (32, 8)
 // ---------------------------------------------------------------------------------------
-__global__ void k_shadow_transpose(const float* __restrict__ preds, long long N, int C,
-                                   const int32_t* __restrict__ model_of_slot, float* __restrict__ T) {
+__global__ void k_shadow_transpose(const float* __restrict__ preds, long long ldh, long long N, int C,
+                                   const int32_t* __restrict__ model_of_slot, long long cs, float* __restrict__ T) {
   __shared__ float tile[32][33];
   const int s = blockIdx.z, h = model_of_slot[s];
   const long long n0 = (long long)blockIdx.x * 32;
   const int c0 = blockIdx.y * 32;
-  const float* src = preds + (size_t)h * N * C;
+  const float* src = preds + (size_t)h * ldh;
   for (int r = threadIdx.y; r < 32; r += 8) {
     const long long n = n0 + r;
     const int c = c0 + threadIdx.x;
     tile[r][threadIdx.x] = (n < N && c < C) ? __ldg(src + (size_t)n * C + c) : 0.f;
   }
   __syncthreads();
-  float* dst = T + (size_t)s * C * N;
+  float* dst = T + (size_t)s * C * cs;
   for (int r = threadIdx.y; r < 32; r += 8) {
     const int c = c0 + r;
     const long long n = n0 + threadIdx.x;
-    if (c < C && n < N) dst[(size_t)c * N + n] = tile[threadIdx.x][r];
+    if (c < C && n < N) dst[(size_t)c * cs + n] = tile[threadIdx.x][r];
   }
 }
 
-extern "C" int coda_b200_shadow_build(const float* preds, int H, int64_t N, int C, const int32_t* model_of_slot, int S,
-                                      float* T, coda_stream_t stream) {
-  CODA_CHECK_ARG(preds && model_of_slot && T && S >= 1 && S <= H, "shadow_build: bad arguments");
+extern "C" int coda_b200_shadow_build(const float* preds, int64_t model_stride, int H, int64_t N, int C,
+                                      const int32_t* model_of_slot, int S, int64_t col_stride, float* T,
+                                      coda_stream_t stream) {
+  CODA_CHECK_ARG(preds && model_of_slot && T && S >= 1 && S <= H && col_stride >= N, "shadow_build: bad arguments");
   long long gx = (N + 31) / 32;
   CODA_CHECK_ARG(gx <= 0x7fffffffLL && S <= 65535, "shadow_build: grid too large");
   dim3 grid((unsigned)gx, (unsigned)((C + 31) / 32), (unsigned)S), block(32, 8);
-  k_shadow_transpose<<<grid, block, 0, as_stream(stream)>>>(preds, N, C, model_of_slot, T);
+  k_shadow_transpose<<<grid, block, 0, as_stream(stream)>>>(preds, (long long)model_stride, N, C, model_of_slot,
+                                                            (long long)col_stride, T);
   CODA_LAUNCH_OK("k_shadow_transpose");
   return CODA_B200_OK;
-}
-
-// label_terms: turn jvec into the list of (sign, element offset, item stride) gathers pi_rank1 performs.
-//   direct     : sum_h preds[h][n][j_h]                                  -> H terms
-//   ensemble   : with t' = the most common j_h and E[n][c] = sum_h preds[h][n][c],
-//                sum_h preds[h][n][j_h] = E[n][t'] + sum_{h: j_h != t'} (preds[h][n][j_h] - preds[h][n][t'])
-//                -> 2*M terms (M = models that disagree with the majority on the labeled item).
-// A model with a shadow slot is read from T (item stride 1) instead of preds (item stride C).
-// hdr = {nterms, t' or -1}.  The term table is then copied into __constant__ memory so that the gather
-// loop reads it through the uniform/constant path instead of the LSU.
-#define R1_MAXT 2048
-struct R1Term {
-  long long off;   // element offset relative to preds for item 0
-  float sg;        // +1 / -1
-  int str;         // element stride per item: C (reference layout) or 1 (shadow)
-};
-__constant__ R1Term c_terms[R1_MAXT];
-
-__global__ void __launch_bounds__(256) k_label_terms(const int32_t* __restrict__ jvec, int H, int C, long long N,
-                                                     int have_ens, const int32_t* __restrict__ slot_of_model,
-                                                     long long shadow_off, int32_t* __restrict__ hdr,
-                                                     R1Term* __restrict__ terms,
-                                                     unsigned long long* __restrict__ pisum_zero) {
-  for (int c = threadIdx.x; c < C; c += blockDim.x) pisum_zero[c] = 0ull;   // pi_rank1 accumulates into it next
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  int* cnt = reinterpret_cast<int*>(smem_raw);   // [C]
-  __shared__ int s_tp, s_m;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) cnt[c] = 0;
-  __syncthreads();
-  for (int h = threadIdx.x; h < H; h += blockDim.x) atomicAdd(&cnt[jvec[h]], 1);
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int best = -1, bc = 0;
-    for (int c = 0; c < C; ++c)
-      if (cnt[c] > best) { best = cnt[c]; bc = c; }
-    s_tp = bc;
-    s_m = H - best;
-  }
-  __syncthreads();
-  const int tp = s_tp, M = s_m;
-  const bool ens = have_ens && 2 * M < H;
-  // every model contributes 1 (direct), or 0 / 2 (ensemble shortcut) terms: exclusive scan over models, in order
-  __shared__ int wtot[8];
-  __shared__ int s_total;
-  int carry = 0;
-  for (int h0 = 0; h0 < H; h0 += 256) {
-    const int h = h0 + threadIdx.x;
-    const int j = h < H ? jvec[h] : 0;
-    const int n = h < H ? (ens ? (j != tp ? 2 : 0) : 1) : 0;
-    int incl = n;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int v = __shfl_up_sync(CODA_FULL, incl, o);
-      if (lane >= o) incl += v;
-    }
-    if (lane == 31) wtot[warp] = incl;
-    __syncthreads();
-    int off = carry;
-    for (int w = 0; w < warp; ++w) off += wtot[w];
-    int k = off + incl - n;
-    if (n) {
-      const int slot = slot_of_model ? slot_of_model[h] : -1;
-      const long long base = slot >= 0 ? shadow_off + (long long)slot * C * N : (long long)h * N * C;
-      const long long mul = slot >= 0 ? N : 1;      // shadow: [slot][class][item]; reference layout: [model][item][class]
-      const int str = slot >= 0 ? 1 : C;
-      terms[k] = R1Term{base + (long long)j * mul, 1.f, str};
-      if (n == 2) terms[k + 1] = R1Term{base + (long long)tp * mul, -1.f, str};
-    }
-    if (threadIdx.x == 255) s_total = off + incl;
-    __syncthreads();
-    carry = s_total;
-  }
-  if (threadIdx.x == 0) {
-    hdr[0] = carry;
-    hdr[1] = ens ? tp : -1;
-  }
 }
 
 // register variant of row_accumulate for C <= 32 * KC: NR rows per call (all loads issued before the first
@@ -749,14 +643,17 @@ __device__ __forceinline__ void rows_accumulate_reg(float* __restrict__ U, long 
 template <int KC>
 __global__ void __launch_bounds__(256) k_pi_rank1(const float* __restrict__ preds, const float* __restrict__ E,
                                                   long long N, int C, const long long* __restrict__ sel,
-                                                  const int32_t* __restrict__ hdr, float lr, float fxs,
+                                                  const int32_t* __restrict__ hdr, const R1Term* __restrict__ gterms,
+                                                  float lr, float fxs,
                                                   float* __restrict__ U, unsigned long long* __restrict__ pisum_fx,
                                                   uint32_t* __restrict__ flags) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   long long* wacc_all = reinterpret_cast<long long*>(smem_raw);                 // [8][C]
+  R1Term* c_terms = reinterpret_cast<R1Term*>(wacc_all + (size_t)8 * C);        // [nt] gather list (broadcast reads)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t = (int)sel[1];
   const int nt = hdr[0], tp = hdr[1];
+  for (int k = threadIdx.x; k < nt; k += blockDim.x) c_terms[k] = gterms[k];
   long long* wacc = wacc_all + (size_t)warp * C;
   for (int c = lane; c < C; c += 32) wacc[c] = 0;
   long long racc[KC > 0 ? KC : 1];
@@ -814,27 +711,16 @@ __global__ void __launch_bounds__(256) k_pi_rank1(const float* __restrict__ pred
   if (bad) atomicOr(flags, bad);
 }
 
-extern "C" int coda_b200_pi_rank1(const float* preds, const float* ens, const float* shadow,
-                                  const int32_t* slot_of_model, int H, int64_t N, int C, const int64_t* sel,
-                                  const int32_t* jvec, double lr, int fx_shift, int32_t* terms /*[2 + 8H]*/, float* U,
+extern "C" int coda_b200_pi_rank1(const float* preds, const float* ens, int H, int64_t N, int C, const int64_t* sel,
+                                  double lr, int fx_shift, const int32_t* terms /*[2 + 8H]*/, float* U,
                                   int64_t* pisum_fx, uint32_t* flags, int ctas_per_sm, coda_stream_t stream) {
-  CODA_CHECK_ARG(preds && sel && jvec && terms && U && pisum_fx && flags, "pi_rank1: null pointer");
+  CODA_CHECK_ARG(preds && sel && terms && U && pisum_fx && flags, "pi_rank1: null pointer");
   CODA_CHECK_ARG(2 * H <= R1_MAXT, "pi_rank1: H=%d too large", H);
   CODA_CHECK_ARG((reinterpret_cast<uintptr_t>(terms) & 7) == 0, "pi_rank1: terms must be 8-byte aligned");
-  CODA_CHECK_ARG(!shadow || slot_of_model, "pi_rank1: shadow needs slot_of_model");
-  int32_t* hdr = terms;                                            // 2 ints
-  R1Term* tlist = reinterpret_cast<R1Term*>(terms + 2);            // 2H x 16 bytes
-  CODA_CHECK_ARG((size_t)C * 4 <= 48 * 1024, "pi_rank1: C=%d too large", C);
+  const int32_t* hdr = terms;                                                  // 2 ints
+  const R1Term* tlist = reinterpret_cast<const R1Term*>(terms + 2);            // <= 2H x 16 bytes
   cudaStream_t st = as_stream(stream);
-  const long long shadow_off = shadow ? (long long)(shadow - preds) : 0;   // both 4-byte aligned device pointers
-  k_label_terms<<<1, 256, (size_t)C * 4, st>>>(jvec, H, C, (long long)N, ens != nullptr,
-                                                shadow ? slot_of_model : nullptr, shadow_off, hdr, tlist,
-                                                reinterpret_cast<unsigned long long*>(pisum_fx));
-  CODA_LAUNCH_OK("k_label_terms");
-  static thread_local void* d_terms = nullptr;
-  if (!d_terms) CODA_CUDA_OK(cudaGetSymbolAddress(&d_terms, c_terms));
-  CODA_CUDA_OK(cudaMemcpyAsync(d_terms, tlist, (size_t)2 * H * sizeof(R1Term), cudaMemcpyDeviceToDevice, st));
-  size_t smem = (size_t)8 * C * 8 + R1_TN * 4;
+  size_t smem = (size_t)8 * C * 8 + (size_t)2 * H * sizeof(R1Term);
   CODA_CHECK_ARG(smem <= 200 * 1024, "pi_rank1: C=%d too large", C);
   long long want = (N + R1_TN - 1) / R1_TN;
   if (ctas_per_sm < 1 || ctas_per_sm > 8) ctas_per_sm = 8;
@@ -843,7 +729,7 @@ extern "C" int coda_b200_pi_rank1(const float* preds, const float* ens, const fl
   do {                                                                                                         \
     CODA_CUDA_OK(cudaFuncSetAttribute(k_pi_rank1<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     k_pi_rank1<KC><<<grid, 256, smem, st>>>(preds, ens, N, C, reinterpret_cast<const long long*>(sel), hdr,    \
-                                            (float)lr, exp2f((float)fx_shift), U,                              \
+                                            tlist, (float)lr, exp2f((float)fx_shift), U,                       \
                                             reinterpret_cast<unsigned long long*>(pisum_fx), flags);           \
   } while (0)
   if (C <= 32) LAUNCH_R1(1);

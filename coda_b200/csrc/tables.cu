@@ -1,4 +1,4 @@
-// Beta quadrature tables and the P(best) mixture.
+// Beta quadrature tables (the P(best) mixture over classes is in step.cu).
 //
 // The reference (coda.py:77-119) evaluates, for every hypothetical (item b, class c), the
 // pdf / cumulative-trapezoid cdf of H Beta distributions on a 256-node grid.  Only three
@@ -229,75 +229,3 @@ extern "C" int coda_b200_beta_tables(const float* D, const float* grid_x, int H,
   return CODA_B200_OK;
 }
 
-// ---------------------------------------------------------------------------------------
-// mixture: pi_hat = normalise(sum_n pi_hat_xi) (coda.py:232-233), m0[h] = sum_c pi_hat[c] PB[c][h]
-// (coda.py:253 == coda.py:145, the P(best) vector), H_before (coda.py:254) and argmax (coda.py:346).
-// single block.
-// ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_mixture(const long long* __restrict__ pisum_fx, const float* __restrict__ PB,
-                                                 int H, int Hp, int C, float* __restrict__ pi_hat,
-                                                 float* __restrict__ m0, float* __restrict__ hb_out,
-                                                 long long* __restrict__ best_out, uint32_t* __restrict__ flags) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* pis = reinterpret_cast<float*>(smem_raw);   // [C]
-  __shared__ float redv[8];
-  __shared__ int redi[8];
-  __shared__ long long tot_s;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) {
-    long long t = 0;
-    for (int c = 0; c < C; ++c) t += pisum_fx[c];
-    tot_s = t;
-  }
-  __syncthreads();
-  const double tot = (double)tot_s;
-  for (int c = tid; c < C; c += 256) {
-    float p = (float)((double)pisum_fx[c] / tot);
-    pis[c] = p;
-    pi_hat[c] = p;
-  }
-  __syncthreads();
-  float ent = 0.f, bv = -INFINITY;
-  int bi = 0x7fffffff;
-  uint32_t bad = 0;
-  for (int h = tid; h < Hp; h += 256) {
-    float m = 0.f;
-    if (h < H) {
-      for (int c = 0; c < C; ++c) m = fmaf(pis[c], PB[(size_t)c * Hp + h], m);
-      if (!isfinite(m)) bad |= CODA_B200_FLAG_NONFINITE_PBEST;
-      ent += ent_term(m);
-      if (m > bv) { bv = m; bi = h; }
-    }
-    m0[h] = m;
-  }
-  ent = warp_sum(ent);
-  warp_argmax(bv, bi);
-  if (lane == 0) { redv[warp] = ent; }
-  __syncthreads();
-  float e = 0.f;
-  for (int k = 0; k < 8; ++k) e += redv[k];
-  __syncthreads();
-  if (lane == 0) { redv[warp] = bv; redi[warp] = bi; }
-  __syncthreads();
-  if (tid == 0) {
-    float b = redv[0];
-    int i = redi[0];
-    for (int k = 1; k < 8; ++k)
-      if (redv[k] > b || (redv[k] == b && redi[k] < i)) { b = redv[k]; i = redi[k]; }
-    *hb_out = e;
-    *best_out = (i == 0x7fffffff) ? 0 : i;
-  }
-  if (bad) atomicOr(flags, bad);
-}
-
-extern "C" int coda_b200_mixture(const int64_t* pisum_fx, const float* PB, int H, int C, float* pi_hat, float* m0,
-                                 float* h_before, int64_t* best_model, uint32_t* flags, coda_stream_t stream) {
-  CODA_CHECK_ARG(pisum_fx && PB && pi_hat && m0 && h_before && best_model && flags, "mixture: null pointer");
-  const int Hp = (H + 31) / 32 * 32;
-  size_t smem = (size_t)C * 4;
-  CODA_CHECK_ARG(smem <= 48 * 1024, "mixture: C=%d too large", C);
-  k_mixture<<<1, 256, smem, as_stream(stream)>>>(reinterpret_cast<const long long*>(pisum_fx), PB, H, Hp, C, pi_hat, m0,
-                                                 h_before, reinterpret_cast<long long*>(best_model), flags);
-  CODA_LAUNCH_OK("k_mixture");
-  return CODA_B200_OK;
-}

@@ -1,15 +1,23 @@
 """Device-side state and kernel sequencing for one shard of the CODA acquisition path.
 
-PyTorch is used for device memory, streams and (through ``coda_b200.dist``) NCCL -- the
-arithmetic of the hot path is in the C-ABI library (``include/coda_b200.h``).
+PyTorch is used for device memory, streams, CUDA graphs and the construction-time all-reduce -- the arithmetic of
+the hot path and the per-step exchanges between shards are in the C-ABI library (``include/coda_b200.h``).
 
 Modes (what is kept between steps; results are the same):
-  ``incremental``   the normalised P(best | hypothetical) row of every pair is cached; a label of
-                    class t only invalidates the pairs of class t (coda.py:317 touches row t only)
+  ``incremental``   the normalised P(best | hypothetical) row of every row is cached; a label of
+                    class t only invalidates the rows of class t (coda.py:317 touches row t only)
                     and the marginal refresh is the rank-1 column update of coda.py:319.
-  ``recompute``     every step recomputes all pairs from the tables (no row cache).
+  ``recompute``     every step recomputes all rows from the tables (no row cache).
   ``recompute_all`` additionally rebuilds all class tables and re-runs the full slab pass of
                     ``update_pi_hat`` every step -- the reference's literal per-step work.
+
+One acquisition step on the device (host-free loop, ``run_steps``; everything below is ONE CUDA graph):
+
+    step_select   merge block records, exchange with the peers, arg-max, label lookup, D[h][t][p_h] += lr, gather list
+    ---- fork ----  side stream: beta_tables(class t) -> pair_rows(class t)        main: pi_rank1 (marginal refresh)
+    step_mixture  exchange the marginal sums, pi_hat, P(best), H_before, argmax         (needs PB[t] from the side)
+    ---- join ----
+    template_gains + gain_eig   the scoring pass for the NEXT selection -> block records
 """
 from __future__ import annotations
 
@@ -21,11 +29,12 @@ import numpy as np
 import torch
 
 from . import _native as nat
-from .dist import LocalComm
 
 TIE_CAP = 256
+REP_WORDS = 12 + TIE_CAP + TIE_CAP // 2     # [flags | record (8) | tie hdr (2) | pad | tie idx | tie val]
 MODES = ("incremental", "recompute", "recompute_all")
 TABLE_BATCH_BYTES = 512 << 20
+HIST_CAP = 1 << 16
 
 
 def _ptr(t):
@@ -33,9 +42,11 @@ def _ptr(t):
 
 
 class Engine:
+    rep_words = REP_WORDS
+
     def __init__(self, preds: torch.Tensor, *, alpha: float, learning_rate: float, multiplier: float,
                  uniform_prior: bool, hyp_w: float = 1.0, mode: str = "incremental", n_offset: int = 0,
-                 n_global: int | None = None, comm=None):
+                 n_global: int | None = None, world: int = 1, own_stream: bool = False):
         if mode not in MODES:
             raise ValueError(f"mode must be one of {MODES}")
         if not (isinstance(preds, torch.Tensor) and preds.is_cuda):
@@ -43,53 +54,79 @@ class Engine:
                                "there is no CPU path in this package")
         if preds.dtype != torch.float32 or preds.dim() != 3:
             raise TypeError("coda_b200: preds must be a float32 (H, N, C) tensor (coda/datasets.py:14)")
-        if not preds.is_contiguous():
-            raise ValueError("coda_b200: preds must be contiguous (H, N, C)")
-        nat.require_device()
+        H, N, Cc = (int(s) for s in preds.shape)
+        if N < 1:
+            raise ValueError("coda_b200: empty shard (fewer items than shards?)")
+        if not (preds.stride(2) == 1 and preds.stride(1) == Cc and (H == 1 or preds.stride(0) >= N * Cc)):
+            raise ValueError("coda_b200: preds must be (H, N, C) with contiguous items (an N-range view of a "
+                             "contiguous slab is fine)")
         self.lib = nat.load()
-        # sector gathers of the rank-1 refresh: ask for 64-byte L2 fills (the default 128 doubles their DRAM traffic;
-        # streaming kernels measured the same at 64 and 128)
-        nat.check(self.lib.coda_b200_set_l2_fetch_granularity(int(os.environ.get("CODA_B200_L2_FETCH", "64"))), "l2_fetch")
         self.preds = preds
         self.dev = preds.device
-        self.H, self.N, self.C = (int(s) for s in preds.shape)
-        self.Hp = (self.H + 31) // 32 * 32
+        with torch.cuda.device(self.dev):
+            nat.require_device()
+            # sector gathers of the rank-1 refresh: ask for 64-byte L2 fills (the default 128 doubles their DRAM
+            # traffic; streaming kernels measured the same at 64 and 128).  A per-device limit.
+            nat.check(self.lib.coda_b200_set_l2_fetch_granularity(int(os.environ.get("CODA_B200_L2_FETCH", "64"))), "l2_fetch")
+        self.H, self.N, self.C = H, N, Cc
+        self.model_stride = int(preds.stride(0)) if H > 1 else N * Cc
+        self.Hp = (H + 31) // 32 * 32
         self.W = self.Hp // 32
         self.P = 256
+        self.T = Cc * (1 + H)
         self.mode = mode
-        self.comm = comm or LocalComm()
+        self.world = int(world)
         self.n_offset = int(n_offset)
-        self.n_global = int(n_global if n_global is not None else self.N)
+        self.n_global = int(n_global if n_global is not None else N)
         self.lr = float(learning_rate)
         self.hyp_w = float(hyp_w)
         self.prior_strength = 1 - alpha                       # coda.py:189
         self.multiplier = float(multiplier)
         self.uniform_prior = bool(uniform_prior)
-        if self.H > 1024:
+        if H > 1024:
             raise NotImplementedError("coda_b200: H > 1024 models is not supported yet")
-        if self.C > 4096:
+        if Cc > 4096:
             raise NotImplementedError("coda_b200: C > 4096 classes is not supported yet")
         self.fx_shift = max(8, min(40, 62 - math.ceil(math.log2(self.n_global + 1))))
         self.counters = {"launches": 0}
-        # side-stream refresh of the class-t tables/rows concurrently with the marginal pass.  On a full-size shard
-        # both want every SM (the tensor-core CTAs take a whole SM's shared memory) and the overlap is neutral; on
-        # small shards (multi-GPU) the few row tiles leave most SMs to the marginal pass and the two overlap.
-        # CODA_B200_OVERLAP=0/1 forces it; default: decided after the pair structure is known (see _build_pairs).
-        self.overlap_env = os.environ.get("CODA_B200_OVERLAP")
-        self.overlap = self.overlap_env == "1"
+        # CODA_B200_OVERLAP=0: class-t table / row refresh on the main stream instead of a side stream
+        self.overlap = os.environ.get("CODA_B200_OVERLAP", "1") != "0"
+        self.use_graph = os.environ.get("CODA_B200_GRAPH", "1") != "0"
         self.profile, self.profile_only = None, None
-        with torch.cuda.device(self.dev):
+        self.xchg = None                                      # set by the group (dist.py) before the first exchange
+        self._mailbox = None
+        self.stream = torch.cuda.Stream(device=self.dev) if own_stream else None
+        self.side = torch.cuda.Stream(device=self.dev)
+        self.ev_fork, self.ev_join, self.ev_tables = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+        self.graphs = {}
+        self.labels_ptr = None
+        with self._on():
             self._alloc_static()
-            self._construct()
 
     # ------------------------------------------------------------------------------ utils
+    @contextlib.contextmanager
+    def _on(self):
+        """Run the body with this shard's device current and, if it owns one, its stream current."""
+        with torch.cuda.device(self.dev):
+            if self.stream is not None:
+                with torch.cuda.stream(self.stream):
+                    yield
+            else:
+                yield
+
+    def _cur(self):
+        return torch.cuda.current_stream(self.dev)
+
     def _s(self):
-        return torch.cuda.current_stream(self.dev).cuda_stream
+        return self._cur().cuda_stream
+
+    def sync(self):
+        (self.stream or torch.cuda.current_stream(self.dev)).synchronize()
 
     def _call(self, name, *args, n=1):
         prof = self.profile
         if prof is not None and (self.profile_only is None or name in self.profile_only):
-            st = torch.cuda.current_stream(self.dev)
+            st = self._cur()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(st)
             rc = getattr(self.lib, name)(*args)
@@ -101,13 +138,16 @@ class Engine:
         self.counters["launches"] += n
 
     def start_profile(self, only=None):
-        """Bracket every C-ABI launch (or just ``only``) with CUDA events on the launching stream."""
+        """Bracket every C-ABI launch (or just ``only``) with CUDA events on the launching stream (eager steps only)."""
         self.profile, self.profile_only = {}, (set(only) if only else None)
 
     def stop_profile(self):
-        """-> {entry point: (launches, total ms)}; synchronises."""
+        """-> {entry point: (launches, total ms, max ms)}; synchronises."""
         torch.cuda.synchronize(self.dev)
-        out = {k: (len(v), float(sum(a.elapsed_time(b) for a, b in v))) for k, v in (self.profile or {}).items()}
+        out = {}
+        for k, v in (self.profile or {}).items():
+            ts = [a.elapsed_time(b) for a, b in v]
+            out[k] = (len(ts), float(sum(ts)), float(max(ts)))
         self.profile = None
         return out
 
@@ -127,7 +167,7 @@ class Engine:
         self.conf_fx = self._z((H, C, C), torch.int64)
         self.D = self._e((H, C, C), torch.float32)
         self.U = self._e((N, C), torch.float32)
-        self.pisum = self._z((C,), torch.int64)
+        self.pisum = self._z((C,), torch.int64)               # THIS shard's column sums (summed over shards in step_mixture)
         self.grid = torch.linspace(1e-6, 1 - 1e-6, P).to(self.dev)   # coda.py:86, built on the host (trap T1)
         self.dL = self._e((C, H, P), torch.float32)
         self.G0T = self._z((C, P, Hp), torch.float32)
@@ -142,83 +182,128 @@ class Engine:
         self.hb = self._z((1,), torch.float32)
         self.best_model = self._z((1,), torch.int64)
         self.eig = self._e((N,), torch.float32)
-        self.nblocks = int(self.lib.coda_b200_eig_blocks(N))
-        self.partials = self._z((self.nblocks, 5), torch.int64)
-        # report block: one D2H copy per step.  [flags | best rec (5) | tie hdr (2) | tie idx | tie val]
-        self.rep = self._z((8 + TIE_CAP + TIE_CAP // 2,), torch.int64)
+        self.nblocks = int(self.lib.coda_b200_eig_blocks(N, H, C))
+        self.partials = self._z((self.nblocks, nat.REC_WORDS), torch.int64)
+        # report block: one D2H copy per API step.  [flags | record (8) | tie hdr (2) | pad | tie idx | tie val]
+        self.rep = self._z((REP_WORDS,), torch.int64)
         self.flags = self.rep[0:1].view(torch.int32)[0:1]
-        self.bestrec = self.rep[1:6]
-        self.tie_hdr = self.rep[6:8]
-        self.tie_idx = self.rep[8:8 + TIE_CAP]
-        self.tie_val = self.rep[8 + TIE_CAP:].view(torch.float32)[:TIE_CAP]
-        self.rep_host = torch.zeros(self.rep.shape, dtype=torch.int64).pin_memory()
+        self.bestrec = self.rep[1:9]
+        self.tie_hdr = self.rep[9:11]
+        self.tie_idx = self.rep[12:12 + TIE_CAP]
+        self.tie_val = self.rep[12 + TIE_CAP:].view(torch.float32)[:TIE_CAP]
+        self.rep_all = self._z((self.world, REP_WORDS), torch.int64)
+        self.rep_host = torch.zeros((self.world, REP_WORDS), dtype=torch.int64).pin_memory()
         self.sel = self._z((2,), torch.int64)
-        self.sel_host = torch.zeros((2,), dtype=torch.int64).pin_memory()
+        # staging ring for host-chosen (idx, class) records: a slot is rewritten only after its copy has executed
+        self.sel_ring = torch.zeros((8, 2), dtype=torch.int64).pin_memory()
+        self.sel_events = [None] * 8
+        self.sel_pos = 0
         self.jvec = self._z((H,), torch.int32)
         self.terms = self._z((2 + 8 * H + 2,), torch.int64).view(torch.int32)[: 2 + 8 * H]   # 8-byte aligned
+        self.step_ctr = self._z((1,), torch.int64)
+        self.hist_idx = self._z((HIST_CAP,), torch.int64)
+        self.hist_q = self._z((HIST_CAP,), torch.float32)
+        self.hist_tie = self._z((HIST_CAP,), torch.int32)
         # ensemble sums E[n][c] (N*C floats) feed pi_rank1's majority shortcut; CODA_B200_ENS=0 disables it
         self.ens = self._e((N, C), torch.float32) if os.environ.get("CODA_B200_ENS", "1") != "0" else None
         cls_per_batch = max(1, min(C, TABLE_BATCH_BYTES // max(1, self.lib.coda_b200_tables_scratch_bytes(H, 1))))
         self.table_batch = int(cls_per_batch)
         self.scratch = self._e((int(self.lib.coda_b200_tables_scratch_bytes(H, self.table_batch)),), torch.uint8)
 
-    # ---------------------------------------------------------------------- construction
-    def _construct(self):
-        H, N, C, s = self.H, self.N, self.C, self._s()
-        self._call("coda_b200_scan_slab", _ptr(self.preds), H, N, C, _ptr(self.hard), _ptr(self.pseudo),
-                   _ptr(self.disagree), _ptr(self.ens), _ptr(self.flags), s)
-        if C <= 128:
-            order = torch.argsort(self.pseudo).to(torch.int32)      # init-time plumbing: any grouping by label will do
-            self._call("coda_b200_confusion_sorted", _ptr(self.preds), _ptr(self.pseudo), _ptr(order), H, N, C,
-                       self.fx_shift, _ptr(self.conf_fx), s)
-            del order
-        else:
-            self._call("coda_b200_confusion_accum", _ptr(self.preds), _ptr(self.pseudo), H, N, C, self.fx_shift,
-                       _ptr(self.conf_fx), s)
-        self.comm.allreduce_sum_(self.conf_fx)
-        self._call("coda_b200_init_dirichlets", _ptr(self.conf_fx), H, C, self.fx_shift, self.prior_strength,
-                   self.multiplier, int(self.uniform_prior), _ptr(self.D), s)
-        self.conf_fx = None                                     # H*C*C int64, only needed once
-        self._refresh_marginals_full()
-        self._build_pairs()
-        self._build_shadow()
-        self._tables(0, C)
-        self._mixture()
-        self.cache_valid = False     # incremental mode: P(best | hypothetical) rows of every pair are cached
-        self.side = torch.cuda.Stream(device=self.dev)
-        self.ev_fork, self.ev_join, self.ev_tables = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
-        self.pending = None
-        self.scored = False
-        self.check_flags(sync=True)
+    def _make_step_struct(self):
+        st = nat.StepStruct()
+        st.H, st.C, st.N, st.n_offset, st.fx_shift, st.lr = self.H, self.C, self.N, self.n_offset, self.fx_shift, self.lr
+        st.hard, st.labeled, st.D, st.jvec, st.sel = _ptr(self.hard), _ptr(self.labeled), _ptr(self.D), _ptr(self.jvec), _ptr(self.sel)
+        st.terms = _ptr(self.terms)
+        st.slot_of_model = _ptr(self.slot_of_model)
+        st.shadow_off = ((self.shadow.data_ptr() - self.preds.data_ptr()) // 4) if self.shadow is not None else 0
+        st.shadow_col_stride = self.shadow_cs
+        st.model_stride = self.model_stride
+        st.have_ens = 1 if self.ens is not None else 0
+        st.pisum_fx, st.PB, st.pi_hat, st.m0 = _ptr(self.pisum), _ptr(self.PB), _ptr(self.pi_hat), _ptr(self.m0)
+        st.h_before, st.best_model = _ptr(self.hb), _ptr(self.best_model)
+        st.partials, st.nblocks, st.eig, st.bestrec = _ptr(self.partials), self.nblocks, _ptr(self.eig), _ptr(self.bestrec)
+        st.labels_global = None
+        st.hist_idx, st.hist_q, st.hist_tie, st.hist_cap = _ptr(self.hist_idx), _ptr(self.hist_q), _ptr(self.hist_tie), HIST_CAP
+        st.step_ctr = _ptr(self.step_ctr)
+        st.flags = _ptr(self.flags)
+        self.st = st
 
-    def _refresh_marginals_full(self):
+    def _x(self):
+        return self.xchg if (self.xchg is not None and self.world > 1) else None
+
+    # ---------------------------------------------------------------------- construction
+    # phases: scan -> [group: sum conf_fx over shards] -> posterior -> mixture (exchange) -> finish (host sync)
+    def construct_scan(self):
+        with self._on():
+            H, N, C, s = self.H, self.N, self.C, self._s()
+            self._call("coda_b200_scan_slab", _ptr(self.preds), self.model_stride, H, N, C, _ptr(self.hard),
+                       _ptr(self.pseudo), _ptr(self.disagree), _ptr(self.ens), _ptr(self.flags), s)
+            if C <= 128:
+                order = torch.argsort(self.pseudo).to(torch.int32)      # init-time plumbing: any grouping by label will do
+                self._call("coda_b200_confusion_sorted", _ptr(self.preds), self.model_stride, _ptr(self.pseudo),
+                           _ptr(order), H, N, C, self.fx_shift, _ptr(self.conf_fx), s)
+                del order
+            else:
+                self._call("coda_b200_confusion_accum", _ptr(self.preds), self.model_stride, _ptr(self.pseudo), H, N, C,
+                           self.fx_shift, _ptr(self.conf_fx), s)
+
+    def construct_posterior(self):
+        with self._on():
+            H, C, s = self.H, self.C, self._s()
+            self._call("coda_b200_init_dirichlets", _ptr(self.conf_fx), H, C, self.fx_shift, self.prior_strength,
+                       self.multiplier, int(self.uniform_prior), _ptr(self.D), s)
+            self.conf_fx = None                                     # H*C*C int64, only needed once
+            self._marginals_full()
+            self._build_rows()
+            self._build_shadow()
+            self._make_step_struct()
+            self._tables(0, C)
+            self.cache_valid = False     # incremental mode: P(best | hypothetical) rows are cached once scored
+            self.pending = False         # a side-stream refresh the next scoring pass has to join
+            self.scored = False          # block records (`partials`) are current
+            self.reported = False        # the report block in rep_host is (being) produced for the current state
+
+    def construct_mixture(self):
+        with self._on():
+            self._mixture()
+
+    def construct_finish(self):
+        with self._on():
+            self.check_flags(sync=True)
+
+    def _marginals_full(self):
+        """coda.py:226-233 as one streaming pass; leaves THIS shard's column sums in ``pisum``."""
         H, N, C, s = self.H, self.N, self.C, self._s()
-        self._call("coda_b200_pi_full", _ptr(self.preds), _ptr(self.D), H, N, C, _ptr(self.U), s)
-        self.pisum.zero_()
+        self._call("coda_b200_pi_full", _ptr(self.preds), self.model_stride, _ptr(self.D), H, N, C, _ptr(self.U), s)
         self._call("coda_b200_pi_reduce", _ptr(self.U), N, C, self.fx_shift, None, _ptr(self.pisum),
                    _ptr(self.flags), s)
-        self.comm.allreduce_sum_(self.pisum)
 
-    def _build_pairs(self):
-        H, N, C, W, s = self.H, self.N, self.C, self.W, self._s()
+    def _build_rows(self):
+        H, N, C, W, T, s = self.H, self.N, self.C, self.W, self.T, self._s()
         ent_cnt = self._e((N,), torch.int32)
+        heavy_cnt = self._e((N,), torch.int32)
         cls_heavy = self._z((C,), torch.int32)
-        self._call("coda_b200_pair_count", _ptr(self.hard), H, N, C, _ptr(ent_cnt), _ptr(cls_heavy), s)
-        self.ent_off = self._z((N + 1,), torch.int64)
-        torch.cumsum(ent_cnt, 0, out=self.ent_off[1:])          # init-time plumbing
+        self._call("coda_b200_pair_count", _ptr(self.hard), H, N, C, _ptr(ent_cnt), _ptr(heavy_cnt), _ptr(cls_heavy), s)
         heavy = cls_heavy.cpu().numpy().astype(np.int64)        # host sync (construction only)
-        n_ent = int(self.ent_off[-1].item())
+        n_ent = int(ent_cnt.sum(dtype=torch.int64).item())
+        self.n_heavy = int(heavy.sum())
+        self.n_entries = n_ent
+        self.max_entries = int(ent_cnt.max().item())
         per_cls = 1 + H + heavy
         cls_base = np.zeros(C + 1, dtype=np.int64)
         np.cumsum(per_cls, out=cls_base[1:])
-        self.npairs = int(cls_base[-1])
-        self.n_heavy = int(heavy.sum())
-        self.n_entries = n_ent
-        if self.npairs >= 2 ** 31:
-            raise NotImplementedError("coda_b200: more than 2^31 pairs in one shard")
+        self.npairs = int(cls_base[-1])                         # == T + n_heavy
+        if self.npairs >= 2 ** 31 or n_ent >= 2 ** 31:
+            raise NotImplementedError("coda_b200: more than 2^31 rows in one shard")
+        self.ent_off = self._z((N + 1,), torch.int32)
+        self.heavy_off = self._z((N + 1,), torch.int32)
+        torch.cumsum(ent_cnt, 0, out=self.ent_off[1:])          # init-time plumbing
+        torch.cumsum(heavy_cnt, 0, out=self.heavy_off[1:])
+        del ent_cnt, heavy_cnt
         self.cls_base_host = cls_base
         self.cls_base = torch.from_numpy(cls_base).to(self.dev)
-        # tiles of <= 32 (SIMT) or <= 128 (tcgen05) same-class pairs
+        # tiles of <= 32 (SIMT) or <= 128 (tcgen05) same-class work-list positions
         def make_tiles(width):
             nt = (per_cls + width - 1) // width
             tile_off = np.zeros(C + 1, dtype=np.int64)
@@ -234,39 +319,42 @@ class Engine:
         self.tile_off_host = tile_off
         self.tile_off = torch.from_numpy(tile_off).to(self.dev)
         self.ntiles = int(tile_off[-1])
-        if self.overlap_env is None:    # measured: +5 % at 2 GPUs, neutral on one full-size shard
-            self.overlap = self.comm.world > 1 or self.max_cls_tiles * 2 <= int(self.lib.coda_b200_sm_count())
-        self.ent_pair = self._e((max(1, n_ent),), torch.int32)
+        self.ent_row = self._e((max(1, n_ent),), torch.int32)
         self.ent_cls = self._e((max(1, n_ent),), torch.int16)
         self.zmask = self._e((self.npairs, W), torch.int32)
-        self.pair_cls = self._e((self.npairs,), torch.int16)
-        self.pair_item = torch.full((self.npairs,), -1, dtype=torch.int32, device=self.dev)
+        self.row_of = self._e((self.npairs,), torch.int32)
         cursor = self._z((C,), torch.int32)
-        self._call("coda_b200_pair_fill", _ptr(self.hard), H, N, C, _ptr(self.ent_off), _ptr(self.cls_base),
-                   _ptr(cursor), _ptr(self.ent_pair), _ptr(self.ent_cls), _ptr(self.zmask), _ptr(self.pair_cls),
-                   _ptr(self.pair_item), s, n=2)
-        # ELL copy of the per-item lists when the longest one fits a warp (eig_points then needs no offset lookup)
-        max_cnt = int(ent_cnt.max().item()) if N else 0
-        self.ell, self.ell_k = None, 0
-        if 0 < max_cnt <= 32:
-            self.ell_k = (max_cnt + 3) // 4 * 4
-            self.ell = self._e((N, self.ell_k, 2), torch.int32)
-            self._call("coda_b200_ell_build", _ptr(self.ent_off), _ptr(self.ent_pair), _ptr(self.ent_cls), N,
-                       self.ell_k, _ptr(self.ell), s)
-        self.gain = self._z((self.npairs,), torch.float32)
-        self.ph_cache = self._e((self.npairs, self.Hp), torch.float32) if self.mode == "incremental" else None
+        self._call("coda_b200_pair_fill", _ptr(self.hard), H, N, C, _ptr(self.ent_off), _ptr(self.heavy_off),
+                   _ptr(self.cls_base), _ptr(cursor), _ptr(self.ent_row), _ptr(self.ent_cls), _ptr(self.zmask),
+                   _ptr(self.row_of), s, n=2)
+        # gains: template rows always; heavy rows only when nothing is cached (recompute modes)
+        self.gain = self._z((T if self.mode == "incremental" else self.npairs,), torch.float32)
+        self.ph_cache = None
+        if self.mode == "incremental":
+            need = self.npairs * self.Hp * 4
+            free, _total = torch.cuda.mem_get_info(self.dev)
+            if need + (2 << 30) > free + torch.cuda.memory_reserved(self.dev) - torch.cuda.memory_allocated(self.dev):
+                # the row cache does not fit next to the slab: fall back to recomputing the rows every step
+                import warnings
+                warnings.warn(f"coda_b200: row cache of {need / 2 ** 30:.1f} GiB does not fit "
+                              f"({free / 2 ** 30:.1f} GiB free); falling back to mode='recompute'")
+                self.mode = "recompute"
+                self.gain = self._z((self.npairs,), torch.float32)
+            else:
+                self.ph_cache = self._e((self.npairs, self.Hp), torch.float32)
 
     def _build_shadow(self):
         """Class-major shadow copy of as many models as spare HBM allows (least accurate first)."""
-        self.shadow, self.slot_of_model, self.n_shadow = None, None, 0
+        self.shadow, self.slot_of_model, self.n_shadow, self.shadow_cs = None, None, 0, 0
         if self.mode == "recompute_all" or os.environ.get("CODA_B200_SHADOW", "1") == "0":
             return
         H, N, C = self.H, self.N, self.C
+        cs = (N + 3) // 4 * 4                                   # every (slot, class) column starts 16-byte aligned
         torch.cuda.synchronize(self.dev)
         torch.cuda.empty_cache()
         free, _total = torch.cuda.mem_get_info(self.dev)
         reserve = int(float(os.environ.get("CODA_B200_SHADOW_RESERVE_GB", "8")) * 2 ** 30)
-        per_model = N * C * 4
+        per_model = cs * C * 4
         S = int(min(H, max(0, (free - reserve) // per_model)))
         cap = os.environ.get("CODA_B200_SHADOW_MODELS")
         if cap is not None:
@@ -282,13 +370,19 @@ class Engine:
         order = torch.argsort(dis, descending=True, stable=True)[:S].to(torch.int32)
         slot = torch.full((H,), -1, dtype=torch.int32, device=self.dev)
         slot[order.long()] = torch.arange(S, dtype=torch.int32, device=self.dev)
-        self.shadow = self._e((S, C, N), torch.float32)
-        self._call("coda_b200_shadow_build", _ptr(self.preds), H, N, C, _ptr(order), S, _ptr(self.shadow), self._s())
-        self.slot_of_model, self.n_shadow = slot, S
+        self.shadow = self._e((S, C, cs), torch.float32)
+        self._call("coda_b200_shadow_build", _ptr(self.preds), self.model_stride, H, N, C, _ptr(order), S, cs,
+                   _ptr(self.shadow), self._s())
+        self.slot_of_model, self.n_shadow, self.shadow_cs = slot, S, cs
 
-    # ------------------------------------------------------------------------ step pieces
-    def _tables(self, lo, hi):
+    # ------------------------------------------------------------------------ step pieces (enqueue only)
+    def _tables(self, lo, hi, sel=False):
         H, C, s = self.H, self.C, self._s()
+        if sel:
+            self._call("coda_b200_beta_tables", _ptr(self.D), _ptr(self.grid), H, C, self.P, self.hyp_w, 0, 1,
+                       _ptr(self.sel), _ptr(self.scratch), _ptr(self.dL), _ptr(self.G0T), _ptr(self.G1T),
+                       _ptr(self.PB), _ptr(self.dLb), _ptr(self.Gb), _ptr(self.flags), s, n=3)
+            return
         for b0 in range(lo, hi, self.table_batch):
             b1 = min(hi, b0 + self.table_batch)
             self._call("coda_b200_beta_tables", _ptr(self.D), _ptr(self.grid), H, C, self.P, self.hyp_w, b0, b1, None,
@@ -296,8 +390,7 @@ class Engine:
                        _ptr(self.dLb), _ptr(self.Gb), _ptr(self.flags), s, n=3)
 
     def _mixture(self):
-        self._call("coda_b200_mixture", _ptr(self.pisum), _ptr(self.PB), self.H, self.C, _ptr(self.pi_hat),
-                   _ptr(self.m0), _ptr(self.hb), _ptr(self.best_model), _ptr(self.flags), self._s())
+        self._call("coda_b200_step_mixture", self.st, self._x(), self._s())
 
     def _pair_rows(self, tile_lo, tile_hi, gains=True, sel=False):
         tail = (_ptr(self.PB), _ptr(self.m0) if gains else None, _ptr(self.pi_hat) if gains else None, self.H,
@@ -305,165 +398,265 @@ class Engine:
                 _ptr(self.tile_off) if sel else None, _ptr(self.flags), self._s())
         if self.use_tc:
             self._call("coda_b200_pair_rows_tc", _ptr(self.tiles), int(tile_lo), int(tile_hi), _ptr(self.zmask),
-                       _ptr(self.dLb), _ptr(self.Gb), *tail)
+                       _ptr(self.row_of), _ptr(self.dLb), _ptr(self.Gb), *tail)
         else:
             self._call("coda_b200_pair_rows", _ptr(self.tiles), int(tile_lo), int(tile_hi), _ptr(self.zmask),
-                       _ptr(self.dL), _ptr(self.G0T), _ptr(self.G1T), *tail)
+                       _ptr(self.row_of), _ptr(self.dL), _ptr(self.G0T), _ptr(self.G1T), *tail)
 
-    def _pair_gain(self, filt, cls=None, on_dev=False):
-        self._call("coda_b200_pair_gain", _ptr(self.ph_cache), _ptr(self.pair_cls), self.npairs, self.H,
-                   _ptr(self.PB), _ptr(self.m0), _ptr(self.pi_hat), _ptr(self.gain),
-                   _ptr(self.sel) if on_dev else None, _ptr(self.cls_base), int(cls or 0), filt, self._s())
-
-    def post_label(self, idx_global: int | None = None, true_class: int | None = None, device_sel: bool = False):
-        """coda.py:316-319: posterior update + marginal refresh + the tables that depend on them.
-        ``device_sel``: the {local idx, class} record is already in ``self.sel`` on the device (host-free loop).
-
-        incremental mode: the class-t tables and the cached rows of the class-t pairs only need the new D, so
-        they are rebuilt on a side stream (FP32-pipe bound) while the main stream does the HBM-bound marginal
-        refresh; the two join before the mixture."""
-        H, N, C, s = self.H, self.N, self.C, self._s()
-        if not device_sel:
-            loc = idx_global - self.n_offset
-            self.sel_host[0] = loc if 0 <= loc < N else -1
-            self.sel_host[1] = true_class
-            self.sel.copy_(self.sel_host, non_blocking=True)
-        self._call("coda_b200_label_row", _ptr(self.hard), H, N, _ptr(self.sel), _ptr(self.jvec), _ptr(self.labeled), s)
-        if self.comm.world > 1:
-            self.comm.share_jvec_(self.jvec, self.sel)
-        self._call("coda_b200_label_apply", _ptr(self.D), H, C, _ptr(self.sel), _ptr(self.jvec), self.lr, s)
-        if self.mode == "recompute_all":
-            self._refresh_marginals_full()
-            self._tables(0, C)
-        else:
-            main = torch.cuda.current_stream(self.dev)
-            overlap = self.overlap and self.mode == "incremental" and self.cache_valid
-            if overlap:
-                self.ev_fork.record(main)
-                self.side.wait_event(self.ev_fork)
-                ctx = torch.cuda.stream(self.side)
-            else:
-                ctx = contextlib.nullcontext()
-            with ctx:
-                if device_sel:
-                    self._call("coda_b200_beta_tables", _ptr(self.D), _ptr(self.grid), H, C, self.P, self.hyp_w, 0, 1,
-                               _ptr(self.sel), _ptr(self.scratch), _ptr(self.dL), _ptr(self.G0T), _ptr(self.G1T),
-                               _ptr(self.PB), _ptr(self.dLb), _ptr(self.Gb), _ptr(self.flags), self._s(), n=3)
-                else:
-                    self._tables(true_class, true_class + 1)
-                if self.mode == "incremental" and self.cache_valid:
-                    # refresh the cached rows of the class-t pairs (no gains: m0 / pi_hat are not final yet)
-                    if overlap:
-                        self.ev_tables.record(self.side)
-                    if device_sel:
-                        self._pair_rows(0, self.max_cls_tiles, gains=False, sel=True)
-                    else:
-                        self._pair_rows(self.tile_off_host[true_class], self.tile_off_host[true_class + 1], gains=False)
-            self._call("coda_b200_pi_rank1", _ptr(self.preds), _ptr(self.ens), _ptr(self.shadow),
-                       _ptr(self.slot_of_model), H, N, C, _ptr(self.sel), _ptr(self.jvec), self.lr, self.fx_shift,
-                       _ptr(self.terms), _ptr(self.U), _ptr(self.pisum), _ptr(self.flags),
-                       4 if overlap else 8, s, n=3)
-            self.comm.allreduce_sum_(self.pisum)
-            if overlap:
-                self.ev_join.record(self.side)
-                main.wait_event(self.ev_tables)     # the mixture needs PB[t]; the rows are awaited in score()
-                self.pending = (None if device_sel else int(true_class), bool(device_sel))
-        self._mixture()
-        self.scored = False
-
-    def score(self, ties=True):
-        """coda.py:235-281 + 306-309: EIG of every item, candidate arg-max, isclose tie scan (enqueue only).
-        ``ties=False`` (host-free loop): stop after the merged arg-max record."""
+    def _score(self):
+        """coda.py:235-281 + the per-block arg-max of coda.py:306/309 -> ``partials``."""
         if self.scored:
             return
-        N, C, s = self.N, self.C, self._s()
         if self.mode == "incremental":
             if not self.cache_valid:
                 self._pair_rows(0, self.ntiles, gains=False)    # fill the row cache once
                 self.cache_valid = True
-            if self.pending is None:
-                self._pair_gain(0)
-            else:   # gains of every other class while the side stream still rebuilds the class-t rows
-                cls, on_dev = self.pending
-                self._pair_gain(1, cls, on_dev)
-                torch.cuda.current_stream(self.dev).wait_event(self.ev_join)
-                self._pair_gain(2, cls, on_dev)
-                self.pending = None
+            if self.pending:
+                self._cur().wait_event(self.ev_join)            # the class-t rows of the side stream
+                self.pending = False
+            self._call("coda_b200_template_gains", _ptr(self.ph_cache), self.H, self.C, _ptr(self.PB), _ptr(self.m0),
+                       _ptr(self.pi_hat), _ptr(self.gain), self._s())
         else:
+            if self.pending:
+                self._cur().wait_event(self.ev_join)
+                self.pending = False
             self._pair_rows(0, self.ntiles)
-        self._call("coda_b200_eig_points", _ptr(self.U), N, C, _ptr(self.ent_off), _ptr(self.ent_pair),
-                   _ptr(self.ent_cls), _ptr(self.gain), _ptr(self.cls_base), _ptr(self.labeled), _ptr(self.disagree),
-                   self.n_offset, _ptr(self.ell), self.ell_k, _ptr(self.eig), _ptr(self.partials), _ptr(self.flags), s)
-        self._call("coda_b200_select_merge", _ptr(self.partials), self.nblocks, _ptr(self.bestrec), s)
-        if self.comm.world > 1:
-            recs = self.comm.allgather(self.bestrec)            # (world, 5)
-            self._call("coda_b200_select_merge", _ptr(recs), self.comm.world, _ptr(self.bestrec), s)
-        if not ties:
-            return
-        self._call("coda_b200_ties", _ptr(self.eig), N, _ptr(self.labeled), _ptr(self.disagree), self.n_offset,
-                   _ptr(self.bestrec), TIE_CAP, _ptr(self.tie_hdr), _ptr(self.tie_idx), _ptr(self.tie_val), s, n=2)
-        if self.comm.world > 1:
-            self.rep_all = self.comm.allgather(self.rep)        # every rank's tie list, judged against the global best
+        self._call("coda_b200_gain_eig", _ptr(self.U), self.N, self.C, self.H, _ptr(self.ent_off), _ptr(self.heavy_off),
+                   _ptr(self.ent_row), _ptr(self.ent_cls), _ptr(self.ph_cache), _ptr(self.gain), _ptr(self.PB),
+                   _ptr(self.m0), _ptr(self.pi_hat), _ptr(self.labeled), _ptr(self.disagree), self.n_offset,
+                   _ptr(self.eig), _ptr(self.partials), _ptr(self.flags), self._s())
         self.scored = True
 
-    def device_step(self, labels_dev: torch.Tensor, step: int, hist_idx=None, hist_q=None):
-        """One acquisition step with no host round trip (bench ``value`` loop): score, pick the lowest tied
-        index, look the label up on the device (coda/oracle.py:23-24), update the posterior.  The pick is the merged
-        arg-max record (first index wins on equal values, coda.py:309); the isclose tie rule needs the host RNG and
-        is part of the API path only."""
-        self.score(ties=False)
-        self._call("coda_b200_device_pick", None, _ptr(self.bestrec), _ptr(labels_dev), self.n_offset, self.N,
-                   _ptr(self.eig), _ptr(self.sel), _ptr(hist_idx), _ptr(hist_q), int(step), self._s())
-        self.post_label(device_sel=True)
+    def _post_label(self):
+        """coda.py:317-319 after ``sel`` / ``jvec`` / D / the gather list are in place (step_select or step_label):
+        marginal refresh + the tables that depend on the new D.  incremental / recompute: the class-t tables (and the
+        cached rows of the class-t work list) only need the new D, so they are rebuilt on a side stream while the main
+        stream does the HBM-bound marginal refresh; the mixture waits for the tables, the next scoring pass for the rows."""
+        H, N, C, s = self.H, self.N, self.C, self._s()
+        self.scored = False
+        self.reported = False
+        if self.mode == "recompute_all":
+            self._call("coda_b200_pi_full", _ptr(self.preds), self.model_stride, _ptr(self.D), H, N, C, _ptr(self.U), s)
+            self._call("coda_b200_pi_reduce", _ptr(self.U), N, C, self.fx_shift, None, _ptr(self.pisum), _ptr(self.flags), s)
+            self._tables(0, C)
+            self._mixture()
+            return
+        main = self._cur()
+        refresh_rows = self.mode == "incremental" and self.cache_valid
+        fork = self.overlap
+        if fork:
+            self.ev_fork.record(main)
+            self.side.wait_event(self.ev_fork)
+            ctx = torch.cuda.stream(self.side)
+        else:
+            ctx = contextlib.nullcontext()
+        with ctx:
+            self._tables(0, 1, sel=True)
+            if fork:
+                self.ev_tables.record(self.side)
+            if refresh_rows:     # cached rows of the class-t work list (no gains: m0 / pi_hat are not final yet)
+                self._pair_rows(0, self.max_cls_tiles, gains=False, sel=True)
+            if fork:
+                self.ev_join.record(self.side)
+        self._call("coda_b200_pi_rank1", _ptr(self.preds), _ptr(self.ens), H, N, C, _ptr(self.sel), self.lr,
+                   self.fx_shift, _ptr(self.terms), _ptr(self.U), _ptr(self.pisum), _ptr(self.flags),
+                   4 if fork else 8, s)
+        if fork:
+            main.wait_event(self.ev_tables)     # the mixture needs PB[t]; the rows are awaited by the scoring pass
+            self.pending = True
+        self._mixture()
+
+    # ------------------------------------------------------------------------ host-free loop
+    def _bind_labels(self, labels_dev):
+        if labels_dev.data_ptr() != self.labels_ptr:
+            if labels_dev.dtype != torch.int64 or labels_dev.device != self.dev or labels_dev.numel() < self.n_global:
+                raise ValueError("labels_dev must be an int64 tensor of all n_global labels on this shard's device")
+            self.st.labels_global = labels_dev.data_ptr()
+            self.labels_ptr = labels_dev.data_ptr()
+            self._labels_keep = labels_dev
+            self.graphs.pop("loop", None)
+
+    def _loop_body(self):
+        """select -> posterior update -> scoring pass for the next selection (one graph)."""
+        self._call("coda_b200_step_select", self.st, self._x(), self._s())
+        self._post_label()
+        self._score()
+
+    def device_step(self, labels_dev: torch.Tensor, step: int | None = None, hist_idx=None, hist_q=None):
+        """One acquisition step with no host round trip: pick the arg-max (first index on equal values, coda.py:309;
+        an isclose tie that the reference would break with random.choice is recorded in ``hist_tie``), look the label
+        up on the device (coda/oracle.py:23-24), update the posterior, score the next selection.  Eager launches; see
+        ``run_steps`` for the CUDA-graph loop.  ``hist_idx`` / ``hist_q``: optional caller-owned history (slot = step)."""
+        with self._on():
+            self._bind_labels(labels_dev)
+            if step is not None:
+                self.step_ctr.fill_(int(step))
+            self._score()
+            self._loop_body()
+            if hist_idx is not None and step is not None:
+                hist_idx[step] = self.hist_idx[int(step) % HIST_CAP]
+                if hist_q is not None:
+                    hist_q[step] = self.hist_q[int(step) % HIST_CAP]
+
+    # The graph loop in phases, so that a front end driving several shards from one thread never blocks on a shard
+    # whose peers have not been enqueued yet: prepare (no exchange inside) -> one eager step -> capture -> replays.
+    def loop_prepare(self, labels_dev: torch.Tensor):
+        with self._on():
+            self._bind_labels(labels_dev)
+            self._score()
+
+    def loop_ready(self) -> bool:
+        return (not self.use_graph) or self.graphs.get("loop") is not None
+
+    def loop_eager(self):
+        with self._on():
+            self._loop_body()
+
+    def loop_capture(self):
+        with self._on():
+            self.graphs["loop"], self.launches_per_step = self._capture(self._loop_body)
+
+    def loop_replay(self, k: int = 1):
+        with self._on():
+            g = self.graphs.get("loop")
+            for _ in range(k):
+                if g is None:
+                    self._loop_body()
+                else:
+                    g.replay()
+            if g is not None:
+                self.counters["launches"] += k * self.launches_per_step
+
+    def run_steps(self, k: int, labels_dev: torch.Tensor):
+        """``k`` acquisition steps as ``k`` replays of one captured CUDA graph (replaces the
+        host loop of main.py:89-94 for offline runs).  History: ``hist_idx/hist_q/hist_tie[step_ctr % HIST_CAP]``."""
+        if k <= 0:
+            return
+        self.loop_prepare(labels_dev)
+        if not self.loop_ready():
+            self.loop_eager()                                   # warm-up (module loading, attributes) outside capture
+            k -= 1
+            self.loop_capture()
+        self.loop_replay(k)
+
+    def _capture(self, body):
+        torch.cuda.synchronize(self.dev)
+        g = torch.cuda.CUDAGraph()
+        cap_stream = self.stream or torch.cuda.Stream(device=self.dev)
+        before = self.counters["launches"]
+        if self.pending:                                        # join eager side-stream work before the capture starts
+            self._cur().wait_event(self.ev_join)
+            self.pending = False
+        self.scored = False
+        with torch.cuda.graph(g, stream=cap_stream, capture_error_mode="relaxed"):
+            body()
+            if self.pending:                                    # every forked stream has to rejoin inside the capture
+                self._cur().wait_event(self.ev_join)
+                self.pending = False
+        launches = self.counters["launches"] - before
+        self.counters["launches"] = before
+        torch.cuda.synchronize(self.dev)
+        return g, launches
+
+    # ------------------------------------------------------------------------ API path
+    def _report(self):
+        """coda.py:306-309: global record + isclose tie list of every shard -> pinned host block (enqueue only)."""
+        self._score()
+        N, s = self.N, self._s()
+        self._call("coda_b200_step_merge", self.st, self._x(), s)
+        self._call("coda_b200_ties", _ptr(self.eig), N, _ptr(self.labeled), _ptr(self.disagree), self.n_offset,
+                   _ptr(self.bestrec), TIE_CAP, _ptr(self.tie_hdr), _ptr(self.tie_idx), _ptr(self.tie_val), s, n=2)
+        self._call("coda_b200_report_gather", _ptr(self.rep), REP_WORDS, _ptr(self.rep_all), self._x(), _ptr(self.flags), s)
+        self.rep_host.copy_(self.rep_all, non_blocking=True)
+        self.reported = True
+
+    def report(self):
+        with self._on():
+            if not self.reported:
+                self._report()
+
+    def _api_body(self):
+        self._call("coda_b200_step_label", self.st, self._x(), self._s())
+        self._post_label()
+        self._report()
+
+    def label(self, idx_global: int, true_class: int, eager_report: bool = True):
+        """coda.py:316-319 for a host-chosen (idx, class): stage the record, posterior update, marginal refresh and --
+        so that the next get_next_item_to_label only has to wait -- the next scoring pass + report.  Enqueue only."""
+        with self._on():
+            k = self.sel_pos
+            self.sel_pos = (k + 1) % len(self.sel_events)
+            if self.sel_events[k] is not None:
+                self.sel_events[k].synchronize()                # the copy that last used this slot has executed
+            loc = idx_global - self.n_offset
+            self.sel_ring[k, 0] = loc if 0 <= loc < self.N else -1
+            self.sel_ring[k, 1] = true_class
+            self.sel.copy_(self.sel_ring[k], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self._cur())
+            self.sel_events[k] = ev
+            if not eager_report:
+                self._call("coda_b200_step_label", self.st, self._x(), self._s())
+                self._post_label()
+                return
+            if self.use_graph and (self.cache_valid or self.mode != "incremental"):
+                g = self.graphs.get("api")
+                if g is None and self.graphs.get("api_warm", 0) >= 2:
+                    g, self.launches_per_api_step = self._capture(self._api_body)
+                    self.graphs["api"] = g
+                if g is not None:
+                    if self.pending:
+                        self._cur().wait_event(self.ev_join)
+                        self.pending = False
+                    g.replay()
+                    self.counters["launches"] += self.launches_per_api_step
+                    self.scored, self.reported = True, True
+                    return
+                self.graphs["api_warm"] = self.graphs.get("api_warm", 0) + 1
+            self._api_body()
 
     def fetch(self):
-        """One D2H copy of the report block + a stream sync.  Returns a dict of host values."""
-        if self.comm.world > 1:
-            return self._fetch_sharded()
-        self.rep_host.copy_(self.rep, non_blocking=True)
-        torch.cuda.current_stream(self.dev).synchronize()
-        r = self.rep_host.numpy()
-        flags = int(r[0:1].view(np.int32)[0])
-        use_a = int(r[3]) > 0
-        bits = int(r[1] if use_a else r[4])
-        best_val = float(np.array([bits & 0xFFFFFFFF], dtype=np.uint32).view(np.float32)[0])
-        best_idx = int(r[2] if use_a else r[5])
-        n_ties = int(r[6])
-        k = min(n_ties, TIE_CAP)
-        tie_idx = r[8:8 + k].copy()
-        tie_val = r[8 + TIE_CAP:].view(np.float32)[:k].copy()
-        return dict(flags=flags, use_a=use_a, n_cand=int(r[3]), best_val=best_val, best_idx=best_idx,
-                    n_ties=n_ties, tie_min=int(r[7]), tie_idx=tie_idx, tie_val=tie_val)
-
-    def _fetch_sharded(self):
-        if getattr(self, "rep_all_host", None) is None or self.rep_all_host.shape != self.rep_all.shape:
-            self.rep_all_host = torch.zeros(self.rep_all.shape, dtype=torch.int64).pin_memory()
-        self.rep_all_host.copy_(self.rep_all, non_blocking=True)
-        torch.cuda.current_stream(self.dev).synchronize()
-        allr = self.rep_all_host.numpy()                        # (world, len(rep))
+        """Wait for the report block and decode it.  Returns a dict of host values."""
+        with self._on():
+            if not self.reported:
+                self._report()
+            self._cur().synchronize()
+        allr = self.rep_host.numpy()                            # (world, REP_WORDS)
         r0 = allr[0]
         flags = 0
         for r in allr:
             flags |= int(r[0:1].view(np.int32)[0])
-        use_a = int(r0[3]) > 0                                  # bestrec is the merged (global) record on every rank
+        use_a = int(r0[3]) > 0                                  # the record is the merged (global) one on every shard
         bits = int(r0[1] if use_a else r0[4])
         best_val = float(np.array([bits & 0xFFFFFFFF], dtype=np.uint32).view(np.float32)[0])
-        n_ties = int(sum(int(r[6]) for r in allr))
+        n_ties = int(sum(int(r[9]) for r in allr))
         idxs, vals = [], []
         for r in allr:
-            k = min(int(r[6]), TIE_CAP)
-            idxs.append(r[8:8 + k])
-            vals.append(r[8 + TIE_CAP:].view(np.float32)[:k])
+            k = min(int(r[9]), TIE_CAP)
+            idxs.append(r[12:12 + k])
+            vals.append(r[12 + TIE_CAP:].view(np.float32)[:k])
         return dict(flags=flags, use_a=use_a, n_cand=int(r0[3]), best_val=best_val,
                     best_idx=int(r0[2] if use_a else r0[5]), n_ties=n_ties,
-                    tie_min=int(min(int(r[7]) for r in allr)), tie_idx=np.concatenate(idxs),
-                    tie_val=np.concatenate(vals))
+                    tie_min=int(min(int(r[10]) for r in allr)), tie_idx=np.concatenate(idxs).copy(),
+                    tie_val=np.concatenate(vals).copy())
 
     def check_flags(self, sync=False, flags=None):
         if flags is None:
             flags = int(self.flags.item()) if sync else 0
         if not flags:
             return
+        if flags & nat.FLAG_ROWSUM_WARN:                        # util.py:37-39 prints a warning and carries on
+            print("[WARN] Pbest(beta) normalized rows not normalised")
+            self.flags.bitwise_and_(~nat.FLAG_ROWSUM_WARN)
+            flags &= ~nat.FLAG_ROWSUM_WARN
+            if not flags:
+                return
+        if flags & nat.FLAG_XCHG_TIMEOUT:
+            raise RuntimeError("coda_b200: a shard did not arrive at an exchange within 2 s (peer crashed or not launched)")
+        if flags & nat.FLAG_NO_CANDIDATE:
+            raise RuntimeError("no unlabeled items left to select from")
+        if flags & nat.FLAG_NEGATIVE_PROB:
+            raise RuntimeError("Pbest(beta) normalized has negatives")                 # util.py:33-35
         if flags & nat.FLAG_RANGE_INPUT and not flags & nat.FLAG_NONFINITE_INPUT:
             raise ValueError("coda_b200: dataset.preds must hold post-softmax scores in [0, 1] (coda/datasets.py:6)")
         names = [v for k, v in nat.FLAG_NAMES.items() if flags & k]
@@ -471,17 +664,52 @@ class Engine:
 
     def mark_labeled(self, idx_global: int):
         loc = idx_global - self.n_offset
-        if 0 <= loc < self.N:
-            self.labeled[loc] = 1
-        self.scored = False
+        with self._on():
+            if 0 <= loc < self.N:
+                self.labeled[loc] = 1
+            self.scored = False
+            self.reported = False
 
     # ------------------------------------------------------------------------- read-outs
     def pbest(self) -> torch.Tensor:
-        return self.m0[: self.H].clone().view(1, self.H)        # coda.py:329 -> (1, H)
+        with self._on():
+            return self.m0[: self.H].clone().view(1, self.H)    # coda.py:329 -> (1, H)
 
     def pi_hat_xi(self) -> torch.Tensor:
-        xi = torch.empty_like(self.U)
-        scratch = torch.zeros_like(self.pisum)
-        self._call("coda_b200_pi_reduce", _ptr(self.U), self.N, self.C, self.fx_shift, _ptr(xi), _ptr(scratch),
-                   _ptr(self.flags), self._s())
-        return xi
+        with self._on():
+            xi = torch.empty_like(self.U)
+            scratch = torch.zeros_like(self.pisum)
+            self._call("coda_b200_pi_reduce", _ptr(self.U), self.N, self.C, self.fx_shift, _ptr(xi), _ptr(scratch),
+                       _ptr(self.flags), self._s())
+            return xi
+
+    # ------------------------------------------------------------------------- checkpoint
+    def state_tensors(self):
+        """Everything a resumed run cannot rebuild from the slab alone: the posterior, the
+        un-normalised marginals they imply, the label mask and the device step counter."""
+        return {"D": self.D, "U": self.U, "labeled": self.labeled, "pisum": self.pisum, "step_ctr": self.step_ctr}
+
+    def close(self):
+        self.graphs.clear()
+        if self._mailbox is not None:
+            self._mailbox.close()
+            self._mailbox = None
+
+
+def build_engines(shards, group, **kw):
+    """Construct the shards of one task in lock-step (``shards``: list of (preds, n_offset) on this process).
+    Phase order matters once peers spin on each other: every shard enqueues its mixture before any host sync."""
+    n_global = kw.pop("n_global")
+    own = len(shards) > 1
+    engines = [Engine(p, n_offset=off, n_global=n_global, world=group.world, own_stream=own, **kw) for p, off in shards]
+    for e in engines:
+        e.construct_scan()
+    group.attach(engines)
+    group.allreduce_sum_([e.conf_fx for e in engines])          # coda.py:42 sums over ALL items
+    for e in engines:
+        e.construct_posterior()
+    for e in engines:
+        e.construct_mixture()
+    for e in engines:
+        e.construct_finish()
+    return engines

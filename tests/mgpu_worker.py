@@ -63,6 +63,17 @@ def main():
         allp = [None] * world
         dist.all_gather_object(allp, picks)
         out[mode] = dict(picks=picks, picks_single=picks1, same_on_all_ranks=all(p == picks for p in allp), **errs)
+        # host-free CUDA-graph loop, continuing from the API steps: exchanges inside the kernels over peer memory
+        sh.run_steps(6, ds.labels)
+        hi = sh.history()[0].tolist()
+        allh = [None] * world
+        dist.all_gather_object(allh, hi)
+        out[mode]["loop_same_on_all_ranks"] = all(h == hi for h in allh)
+        if rank == 0:
+            one.run_steps(6, full.labels)
+            out[mode]["loop_picks"], out[mode]["loop_picks_single"] = hi, one.history()[0].tolist()
+            out[mode]["loop_D_equal"] = bool(torch.equal(sh.dirichlets, one.dirichlets))
+            out[mode]["loop_pi_hat_equal"] = bool(torch.equal(sh.pi_hat, one.pi_hat))
     if rank == 0:
         print("MGPU_RESULT " + json.dumps(out), flush=True)
     dist.barrier()

@@ -211,32 +211,47 @@ def test_modes_agree_and_incremental_is_exact():
     assert abs(float(sels["incremental"].pi_hat.sum()) - 1.0) < 1e-5
 
 
-def test_pair_structure_invariants():
+def test_row_structure_invariants():
+    """Entry lists (item-major), heavy rows (contiguous per item, ascending class) and the class-major work list the
+    row kernels tile over (zmask, row_of) describe exactly the hard predictions."""
     from coda_b200.synth import synth
     preds, labels = synth(40, 3000, 12, seed=2, dense=True)
     sel = _mk(preds, labels)
     e = sel.engine
+    H, C, T = e.H, e.C, e.T
     hard = preds.argmax(-1).T.numpy()                                     # (N, H)
     ent_off = e.ent_off.cpu().numpy()
-    ent_pair = e.ent_pair.cpu().numpy()
+    heavy_off = e.heavy_off.cpu().numpy()
+    ent_row = e.ent_row.cpu().numpy()
     ent_cls = e.ent_cls.cpu().numpy().astype(np.int64) & 0xFFFF
     zmask = e.zmask.cpu().numpy().astype(np.int64) & 0xFFFFFFFF
-    pair_cls = e.pair_cls.cpu().numpy().astype(np.int64) & 0xFFFF
+    row_of = e.row_of.cpu().numpy()
     base = e.cls_base_host
+    assert e.npairs == T + e.n_heavy == T + int(heavy_off[-1]) and len(row_of) == e.npairs
+    assert sorted(row_of.tolist()) == list(range(e.npairs))               # the work list is a permutation of the rows
+    pos_of_row = np.empty(e.npairs, dtype=np.int64)
+    pos_of_row[row_of] = np.arange(e.npairs)
+
+    def bits(q):
+        return [h for h in range(H) if (zmask[q, h >> 5] >> (h & 31)) & 1]
+    for c in range(C):                                                    # templates: class-major rows c*(1+H)+k
+        for k in (0, 1, H // 2, H):
+            q = base[c] + k
+            assert row_of[q] == c * (1 + H) + k and bits(q) == ([] if k == 0 else [k - 1])
     for n in list(range(0, 3000, 97)) + [2999]:
         classes = sorted(set(hard[n].tolist()))
         seg = slice(ent_off[n], ent_off[n + 1])
         assert ent_cls[seg].tolist() == classes                           # one entry per distinct class, ascending
-        for c, pid in zip(classes, ent_pair[seg].tolist()):
+        rows = ent_row[seg]
+        heavy_rows = rows[rows >= T]
+        assert heavy_rows.tolist() == list(range(T + heavy_off[n], T + heavy_off[n + 1]))   # contiguous, in entry order
+        for c, row in zip(classes, rows.tolist()):
             members = np.nonzero(hard[n] == c)[0]
-            assert pair_cls[pid] == c and base[c] <= pid < base[c + 1]
-            bits = [h for h in range(e.H) if (zmask[pid, h >> 5] >> (h & 31)) & 1]
-            assert bits == members.tolist()
             if len(members) == 1:
-                assert pid == base[c] + 1 + members[0]                    # singleton template
+                assert row == c * (1 + H) + 1 + members[0]                # singleton template row
             else:
-                assert pid >= base[c] + 1 + e.H and int(e.pair_item[pid]) == n
-    assert int((e.pair_item >= 0).sum()) == e.n_heavy
+                q = pos_of_row[row]
+                assert row >= T and base[c] + 1 + H <= q < base[c + 1] and bits(q) == members.tolist()
 
 
 def test_fixed_point_sums_are_shard_invariant():
@@ -258,9 +273,9 @@ def test_fixed_point_sums_are_shard_invariant():
         dis = torch.empty(n, dtype=torch.uint8, device=dev)
         flags = torch.zeros(1, dtype=torch.int32, device=dev)
         out = torch.zeros((H, C, C), dtype=torch.int64, device=dev)
-        nat.check(lib.coda_b200_scan_slab(p.data_ptr(), H, n, C, hard.data_ptr(), pseudo.data_ptr(), dis.data_ptr(),
+        nat.check(lib.coda_b200_scan_slab(p.data_ptr(), n * C, H, n, C, hard.data_ptr(), pseudo.data_ptr(), dis.data_ptr(),
                                           None, flags.data_ptr(), st))
-        nat.check(lib.coda_b200_confusion_accum(p.data_ptr(), pseudo.data_ptr(), H, n, C, 40, out.data_ptr(), st))
+        nat.check(lib.coda_b200_confusion_accum(p.data_ptr(), n * C, pseudo.data_ptr(), H, n, C, 40, out.data_ptr(), st))
         return out, pseudo
     whole, pseudo = conf(P)
     a, _ = conf(P[:, :2300].contiguous())
@@ -269,8 +284,19 @@ def test_fixed_point_sums_are_shard_invariant():
     # the class-sorted register variant produces the same bits as the shared-memory-atomics variant
     order = torch.argsort(pseudo).to(torch.int32)
     sorted_out = torch.zeros_like(whole)
-    nat.check(lib.coda_b200_confusion_sorted(P.data_ptr(), pseudo.data_ptr(), order.data_ptr(), H, N, C, 40,
+    nat.check(lib.coda_b200_confusion_sorted(P.data_ptr(), N * C, pseudo.data_ptr(), order.data_ptr(), H, N, C, 40,
                                              sorted_out.data_ptr(), st))
+    # an N-range VIEW of the slab (model stride = the full task's) gives the same sums as a contiguous copy of it
+    view, _ = conf(P[:, :2300].contiguous())
+    hard = torch.empty((2300, H), dtype=torch.int16, device=dev)
+    ps2 = torch.empty(2300, dtype=torch.int32, device=dev)
+    dis = torch.empty(2300, dtype=torch.uint8, device=dev)
+    flags = torch.zeros(1, dtype=torch.int32, device=dev)
+    out = torch.zeros((H, C, C), dtype=torch.int64, device=dev)
+    nat.check(lib.coda_b200_scan_slab(P.data_ptr(), N * C, H, 2300, C, hard.data_ptr(), ps2.data_ptr(), dis.data_ptr(),
+                                      None, flags.data_ptr(), st))
+    nat.check(lib.coda_b200_confusion_accum(P.data_ptr(), N * C, ps2.data_ptr(), H, 2300, C, 40, out.data_ptr(), st))
+    assert torch.equal(out, view)
     assert torch.equal(whole, sorted_out)
     ref = torch.einsum("nc,hnj->hcj", torch.nn.functional.one_hot(pseudo.long().cpu(), C).float(), preds)
     np.testing.assert_allclose((whole.double() / 2 ** 40).cpu().numpy(), ref.numpy(), rtol=2e-6, atol=1e-6)

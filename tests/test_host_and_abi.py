@@ -20,9 +20,9 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/coda_b200.h but not exported"
     assert declared == set(nat.SIGNATURES), declared ^ set(nat.SIGNATURES)
-    assert lib.coda_b200_version() == 100
+    assert lib.coda_b200_version() == nat.VERSION == 200
     raw = ctypes.CDLL(nat.lib_path())
-    assert raw.coda_b200_version() == 100
+    assert raw.coda_b200_version() == 200
 
 
 def test_no_gpu_means_loud_failure():
@@ -102,10 +102,9 @@ def _gloo_worker(rank, world, port, q):
     rec = torch.tensor([[0.25, 7, 2, 0.5, 3], [0.25, 5, 1, 0.4, 8]][rank], dtype=torch.float64)
     allr = comm.allgather(rec)
     merged = merge_records([tuple(r.tolist()) for r in allr])
-    # 2. label exchange: only the owner knows p_h(idx); SUM all-reduce with zeros elsewhere
-    jvec = torch.tensor([3, 1, 4, 1, 5], dtype=torch.int32) if rank == 1 else torch.zeros(5, dtype=torch.int32)
-    sel = torch.tensor([12 if rank == 1 else -1, 2], dtype=torch.int64)
-    comm.share_jvec_(jvec, sel)
+    # 2. construction: SUM all-reduce of the soft-confusion sums (coda.py:42), int64 fixed point
+    jvec = torch.tensor([3, 1, 4, 1, 5], dtype=torch.int64) if rank == 1 else torch.zeros(5, dtype=torch.int64)
+    comm.allreduce_sum_(jvec)
     # 3. marginals: exact int64 sums
     pis = torch.tensor([2 ** 40 + rank, 5], dtype=torch.int64)
     comm.allreduce_sum_(pis)

@@ -27,3 +27,5 @@ def test_sharded_equals_single(world):
         assert o["picks"] == o["picks_single"], (mode, o["picks"], o["picks_single"])
         assert o["pi_hat_equal"] and o["D_equal"], mode        # int64 fixed-point statistics: shard-count invariant bits
         assert o["pbest"] < 1e-6 and o["eig"] < 1e-7, (mode, o)
+        assert o["loop_same_on_all_ranks"] and o["loop_picks"] == o["loop_picks_single"], (mode, o)
+        assert o["loop_D_equal"] and o["loop_pi_hat_equal"], mode

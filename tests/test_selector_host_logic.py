@@ -19,6 +19,8 @@ class FakeEngine:
     """Mimics the attributes / calls CODA uses; `script` is a list of reports fetch() returns in order."""
     instances = []
 
+    stream = None
+
     def __init__(self, preds, **kw):
         self.H, self.N, self.C = (int(s) for s in preds.shape)
         self.comm = FakeComm()
@@ -29,8 +31,15 @@ class FakeEngine:
         self.pi_hat = torch.full((self.C,), 1.0 / self.C)
         FakeEngine.instances.append(self)
 
-    def score(self, ties=True):
+    def report(self):
         pass
+
+    def sync(self):
+        pass
+
+    def _on(self):
+        import contextlib
+        return contextlib.nullcontext()
 
     def fetch(self):
         return self.script.pop(0)
@@ -40,7 +49,7 @@ class FakeEngine:
             names = [v for k, v in nat.FLAG_NAMES.items() if flags & k]
             raise RuntimeError(f"[NUMERIC ERROR] {', '.join(names)} has bad values (NaN/Inf)")
 
-    def post_label(self, idx, cls):
+    def label(self, idx, cls, eager_report=True):
         self.posted.append((idx, cls))
 
     def mark_labeled(self, idx):
@@ -64,9 +73,14 @@ def report(ties, vals, flags=0, n_ties=None):
                 tie_val=np.asarray(vals, dtype=np.float32))
 
 
+def fake_build(shards, group, **kw):
+    kw.pop("n_global", None)
+    return [FakeEngine(p, **kw) for p, _off in shards]
+
+
 @pytest.fixture()
 def sel(monkeypatch):
-    monkeypatch.setattr(selmod, "Engine", FakeEngine)
+    monkeypatch.setattr(selmod, "build_engines", fake_build)
     s = selmod.CODA(DS())
     return s, s.engine
 
@@ -126,7 +140,7 @@ def test_no_candidates_and_unknown_acquisition(sel, monkeypatch):
 
 
 def test_from_args_maps_the_cli_namespace(monkeypatch):
-    monkeypatch.setattr(selmod, "Engine", FakeEngine)
+    monkeypatch.setattr(selmod, "build_engines", fake_build)
 
     class A:
         prefilter_n = 7; alpha = 0.8; learning_rate = 0.05; multiplier = 1.5; no_diag_prior = True; q = "eig"

@@ -83,12 +83,13 @@ SIGNATURES = {
     "coda_b200_tables_scratch_bytes": (sz, [i32, i32]),
     "coda_b200_beta_tables": (i32, [p, p, i32, i32, i32, f64, i32, i32, p, p, p, p, p, p, p, p, p, p]),
     "coda_b200_pair_count": (i32, [p, i32, i64, i32, p, p, p, p]),
-    "coda_b200_pair_fill": (i32, [p, i32, i64, i32, p, p, p, p, p, p, p, p, p]),
+    "coda_b200_pair_fill": (i32, [p, i32, i64, i32, p, p, p, p, p, p, p, p, p, p]),
     "coda_b200_pair_rows": (i32, [p, i32, i32, p, p, p, p, p, p, p, p, i32, p, p, p, p, p, p]),
     "coda_b200_pair_rows_tc": (i32, [p, i32, i32, p, p, p, p, p, p, p, i32, p, p, p, p, p, p]),
     "coda_b200_template_gains": (i32, [p, i32, i32, p, p, p, p, p]),
     "coda_b200_eig_blocks": (i32, [i64, i32, i32]),
-    "coda_b200_gain_eig": (i32, [p, i64, i32, i32, p, p, p, p, p, p, p, p, p, p, p, i64, p, p, p, p]),
+    "coda_b200_gain_eig": (i32, [p, i64, i32, i32, p, p, p, p, p, p, p, p, p, p, p, i64, i32, p, p, p, p]),
+    "coda_b200_row_gains": (i32, [p, p, i64, i32, i32, p, p, p, p, p]),
     "coda_b200_step_select": (i32, [PS, PX, p]),
     "coda_b200_step_merge": (i32, [PS, PX, p]),
     "coda_b200_step_label": (i32, [PS, PX, p]),

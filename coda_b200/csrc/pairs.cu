@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(256) k_pair_fill(const uint16_t* __restrict__ 
                                                    const long long* __restrict__ cls_base,
                                                    int32_t* __restrict__ cls_cursor, int32_t* __restrict__ ent_row,
                                                    uint16_t* __restrict__ ent_cls, uint32_t* __restrict__ zmask,
-                                                   int32_t* __restrict__ row_of) {
+                                                   int32_t* __restrict__ row_of, uint16_t* __restrict__ row_cls) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int* cnt_all = reinterpret_cast<int*>(smem_raw);   // [8][C]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -121,7 +121,10 @@ __global__ void __launch_bounds__(256) k_pair_fill(const uint16_t* __restrict__ 
           const long long q = cls_base[c] + 1 + H + slot;     // position in the class-major work list
           row = next_row++;
           if (lane < W) zmask[(size_t)q * W + lane] = myword;
-          if (lane == 0) row_of[q] = row;
+          if (lane == 0) {
+            row_of[q] = row;
+            row_cls[row - C * (H + 1)] = (uint16_t)c;
+          }
         }
         if (lane == 0) {
           ent_row[pos] = row;
@@ -150,8 +153,8 @@ extern "C" int coda_b200_pair_count(const uint16_t* hard, int H, int64_t N, int 
 extern "C" int coda_b200_pair_fill(const uint16_t* hard, int H, int64_t N, int C, const int32_t* ent_off,
                                    const int32_t* heavy_off, const int64_t* cls_base, int32_t* cls_cursor,
                                    int32_t* ent_row, uint16_t* ent_cls, uint32_t* zmask, int32_t* row_of,
-                                   coda_stream_t stream) {
-  CODA_CHECK_ARG(hard && ent_off && heavy_off && cls_base && cls_cursor && ent_row && ent_cls && zmask && row_of,
+                                   uint16_t* row_cls, coda_stream_t stream) {
+  CODA_CHECK_ARG(hard && ent_off && heavy_off && cls_base && cls_cursor && ent_row && ent_cls && zmask && row_of && row_cls,
                  "pair_fill: null pointer");
   CODA_CHECK_ARG(H <= 1024, "pair_fill: H=%d > 1024 not supported", H);
   const int W = (H + 31) / 32;
@@ -164,7 +167,7 @@ extern "C" int coda_b200_pair_fill(const uint16_t* hard, int H, int64_t N, int C
   int grid = (int)min((long long)(N + 7) / 8, (long long)coda_sm_count() * 8);
   k_pair_fill<<<grid, 256, smem, as_stream(stream)>>>(hard, H, N, C, W, ent_off, heavy_off,
                                                       reinterpret_cast<const long long*>(cls_base), cls_cursor,
-                                                      ent_row, ent_cls, zmask, row_of);
+                                                      ent_row, ent_cls, zmask, row_of, row_cls);
   CODA_LAUNCH_OK("k_pair_fill");
   return CODA_B200_OK;
 }

@@ -12,6 +12,8 @@
 #include "common.cuh"
 #include "terms.cuh"
 
+#include <stdlib.h>
+
 // ---------------------------------------------------------------------------------------
 // scan_slab: one pass over the slab.  CTA = tile of TN points, all H models.
 // ---------------------------------------------------------------------------------------
@@ -711,6 +713,290 @@ __global__ void __launch_bounds__(256) k_pi_rank1(const float* __restrict__ pred
   if (bad) atomicOr(flags, bad);
 }
 
+// pi_rank1 with four consecutive items per lane (C <= 128): a warp owns 128 consecutive items, so every gather
+// from the class-major shadow is one 512-byte contiguous run per term (float4 per lane) instead of 128 bytes --
+// four times fewer DRAM page switches for the same bytes.  Same arithmetic, same order as k_pi_rank1.
+#define R1V_WI 128     // items per warp
+template <int KC>
+__global__ void __launch_bounds__(256, 3) k_pi_rank1_v4(const float* __restrict__ preds, const float* __restrict__ E,
+                                                     long long N, int C, const long long* __restrict__ sel,
+                                                     const int32_t* __restrict__ hdr, const R1Term* __restrict__ gterms,
+                                                     float lr, float fxs, float* __restrict__ U,
+                                                     unsigned long long* __restrict__ pisum_fx,
+                                                     uint32_t* __restrict__ flags) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  long long* wacc_all = reinterpret_cast<long long*>(smem_raw);                 // [8][C]
+  R1Term* c_terms = reinterpret_cast<R1Term*>(wacc_all + (size_t)8 * C);        // [nt]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = (int)sel[1];
+  const int nt = hdr[0], tp = hdr[1];
+  for (int k = threadIdx.x; k < nt; k += blockDim.x) c_terms[k] = gterms[k];
+  long long racc[KC];
+#pragma unroll
+  for (int k = 0; k < KC; ++k) racc[k] = 0;
+  __syncthreads();
+  uint32_t bad = 0;
+  const long long cta_items = (long long)8 * R1V_WI;
+  for (long long n0 = (long long)blockIdx.x * cta_items + (long long)warp * R1V_WI; n0 < N; n0 += (long long)gridDim.x * cta_items) {
+    const long long nl = n0 + 4 * lane;
+    const bool full4 = nl + 3 < N;
+    float d[4] = {0.f, 0.f, 0.f, 0.f};
+    if (tp >= 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (nl + i < N) d[i] = __ldg(E + (size_t)(nl + i) * C + tp);
+    }
+    int k = 0;
+    for (; k + 8 <= nt; k += 8) {
+      float v[8][4];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const R1Term tm = c_terms[k + q];
+        if (tm.str == 1 && full4) {
+          const float4 x = __ldg(reinterpret_cast<const float4*>(preds + tm.off + nl));
+          v[q][0] = x.x; v[q][1] = x.y; v[q][2] = x.z; v[q][3] = x.w;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) v[q][i] = (nl + i < N) ? __ldg(preds + tm.off + (nl + i) * tm.str) : 0.f;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float sg = c_terms[k + q].sg;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) d[i] = fmaf(sg, v[q][i], d[i]);
+      }
+    }
+    for (; k < nt; ++k) {
+      const R1Term tm = c_terms[k];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float x = (nl + i < N) ? __ldg(preds + tm.off + (nl + i) * tm.str) : 0.f;
+        d[i] = fmaf(tm.sg, x, d[i]);
+      }
+    }
+    float dl[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dl[i] = lr * d[i];
+    const int rows = (int)min((long long)R1V_WI, N - n0);
+    for (int r = 0; r < rows; r += 4) {
+      float dv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) dv[i] = __shfl_sync(CODA_FULL, dl[i], r >> 2);
+      rows_accumulate_reg<KC, 4>(U, n0 + r, rows - r, 1, C, lane, fxs, t, dv, racc, bad);
+    }
+  }
+  long long* wacc = wacc_all + (size_t)warp * C;
+#pragma unroll
+  for (int k = 0; k < KC; ++k) {
+    const int c = lane + 32 * k;
+    if (c < C) wacc[c] = racc[k];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    long long s2 = 0;
+    for (int w = 0; w < 8; ++w) s2 += wacc_all[(size_t)w * C + c];
+    if (s2) atomicAdd(pisum_fx + c, (unsigned long long)s2);
+  }
+  if (bad) atomicOr(flags, bad);
+}
+
+// ---------------------------------------------------------------------------------------
+// pi_rank1, bulk-TMA pipeline (C <= 128): the same arithmetic in the same order as k_pi_rank1, fed differently.
+// A persistent CTA walks tiles of TR items.  Everything a tile needs is contiguous in HBM:
+//   * the U rows of the tile            TR*C floats   -> ONE cp.async.bulk into shared memory (warp 9)
+//   * per shadow term, the TR increments  TR floats    -> one cp.async.bulk each into a ring of ST stages x TB terms (warp 8)
+// so the memory system runs ahead of the arithmetic without holding anything in registers.  Consumer warp w owns
+// items [32w, 32w+32) of the tile: lane i sums item i's terms in list order (ring slots by LDS, the few terms of
+// models without a shadow slot by a direct gather), then the warp walks its 32 rows of the U tile (increment handed
+// over by shuffle), renormalises, accumulates the int64 column sums in registers and stores column t back.
+// ---------------------------------------------------------------------------------------
+#define R1X_THREADS 320      // 8 consumer warps + ring producer warp + U producer warp
+#define R1X_ST 4
+#define R1X_TB 16
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int KC>
+__global__ void __launch_bounds__(R1X_THREADS, 1) k_pi_rank1_tma(const float* __restrict__ preds,
+                                                                 const float* __restrict__ E, long long N, int C, int TR,
+                                                                 const long long* __restrict__ sel,
+                                                                 const int32_t* __restrict__ hdr,
+                                                                 const R1Term* __restrict__ gterms, float lr, float fxs,
+                                                                 float* __restrict__ U,
+                                                                 unsigned long long* __restrict__ pisum_fx,
+                                                                 uint32_t* __restrict__ flags) {
+  extern __shared__ __align__(128) unsigned char smem_r1x[];
+  unsigned char* smem_raw = smem_r1x;
+  const int nt = hdr[0], tp = hdr[1];
+  const int t = (int)sel[1];
+  const size_t u_bytes = ((size_t)TR * C * 4 + 127) & ~(size_t)127;
+  float* Ut = reinterpret_cast<float*>(smem_raw);                                        // [TR][C]
+  float* ring = reinterpret_cast<float*>(smem_raw + u_bytes);                            // [ST][TB][TR]
+  R1Term* terms = reinterpret_cast<R1Term*>(ring + (size_t)R1X_ST * R1X_TB * TR);        // [nt]
+  long long* wacc_all = reinterpret_cast<long long*>(terms + nt);                        // [8][C]
+  int* shl = reinterpret_cast<int*>(wacc_all + (size_t)8 * C);                           // [nt] indices of the shadow terms
+  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(shl + nt) + 7) & ~(uintptr_t)7);
+  uint64_t* fullU = bars, *emptyU = bars + 1, *full = bars + 2, *empty = bars + 2 + R1X_ST;
+  __shared__ int s_nsh;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nwarp_act = TR >> 5;                                                         // consumer warps with rows
+  for (int k = tid; k < nt; k += R1X_THREADS) terms[k] = gterms[k];
+  for (int c = tid; c < 8 * C; c += R1X_THREADS) wacc_all[c] = 0;
+  if (tid == 0) {
+    mbar_init(fullU, 1);
+    mbar_init(emptyU, nwarp_act);
+    for (int s = 0; s < R1X_ST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], nwarp_act); }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (tid == 0) {                               // shadow terms in list order (cheap: nt <= 2H)
+    int n = 0;
+    for (int k = 0; k < nt; ++k)
+      if (terms[k].str == 1) shl[n++] = k;
+    s_nsh = n;
+  }
+  __syncthreads();
+  const int nsh = s_nsh;
+  const int nch = (nsh + R1X_TB - 1) / R1X_TB;                                            // ring chunks per tile
+  const long long ntiles = (N + TR - 1) / TR;
+
+  if (warp == 8) {                              // ---- ring producer ----
+    if (lane == 0) {
+      long long gch = 0;
+      for (long long ti = blockIdx.x; ti < ntiles; ti += gridDim.x) {
+        const long long n0 = ti * TR;
+        const int rows = (int)min((long long)TR, N - n0);
+        const uint32_t rb = (uint32_t)((rows + 3) & ~3) * 4u;                             // columns are padded to 4 items
+        for (int c = 0; c < nch; ++c, ++gch) {
+          const int s = (int)(gch % R1X_ST);
+          if (gch >= R1X_ST) mbar_wait(&empty[s], (uint32_t)(((gch / R1X_ST) - 1) & 1));
+          const int cnt = min(R1X_TB, nsh - c * R1X_TB);
+          mbar_expect_tx(&full[s], (uint32_t)cnt * rb);
+          for (int j = 0; j < cnt; ++j)
+            tma_load_1d(ring + ((size_t)s * R1X_TB + j) * TR, preds + terms[shl[c * R1X_TB + j]].off + n0, rb, &full[s]);
+        }
+      }
+    }
+    return;
+  }
+  if (warp == 9) {                              // ---- U tile producer ----
+    if (lane == 0) {
+      long long it = 0;
+      for (long long ti = blockIdx.x; ti < ntiles; ti += gridDim.x, ++it) {
+        const long long n0 = ti * TR;
+        const int rows = (int)min((long long)TR, N - n0);
+        const uint32_t ub = ((uint32_t)rows * C * 4u + 15u) & ~15u;                       // U carries 16 bytes of slack
+        if (it > 0) mbar_wait(emptyU, (uint32_t)((it - 1) & 1));
+        mbar_expect_tx(fullU, ub);
+        tma_load_1d(Ut, U + (size_t)n0 * C, ub, fullU);
+      }
+    }
+    return;
+  }
+  if (warp >= nwarp_act) return;
+  // ---- consumers ----
+  long long racc[KC];
+#pragma unroll
+  for (int k = 0; k < KC; ++k) racc[k] = 0;
+  uint32_t bad = 0;
+  long long gch = 0, it = 0;
+  for (long long ti = blockIdx.x; ti < ntiles; ti += gridDim.x, ++it) {
+    const long long n0 = ti * TR;
+    const int rows = (int)min((long long)TR, N - n0);
+    const int li = warp * 32 + lane;                 // this lane's item within the tile
+    const long long n = n0 + li;
+    const bool valid = li < rows;
+    float d = 0.f;
+    if (valid && tp >= 0) d = __ldg(E + (size_t)n * C + tp);
+    int shi = 0;                                     // shadow terms consumed in this tile
+    const float* slot = ring;
+    for (int k = 0; k < nt; ++k) {
+      const R1Term tm = terms[k];
+      float v = 0.f;
+      if (tm.str == 1) {
+        const int j = shi % R1X_TB;
+        if (j == 0) {
+          const long long g = gch + shi / R1X_TB;
+          const int s = (int)(g % R1X_ST);
+          mbar_wait(&full[s], (uint32_t)((g / R1X_ST) & 1));
+          slot = ring + (size_t)s * R1X_TB * TR;
+        }
+        v = slot[(size_t)j * TR + li];
+        ++shi;
+        if (j == R1X_TB - 1 || shi == nsh) {         // last read of this stage by this warp
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[(int)((gch + (shi - 1) / R1X_TB) % R1X_ST)]);
+        }
+      } else if (valid) {
+        v = __ldg(preds + tm.off + n * tm.str);
+      }
+      d = fmaf(tm.sg, v, d);
+    }
+    gch += nch;
+    const float dl = valid ? lr * d : 0.f;
+    // ---- row pass over this warp's 32 rows of the U tile ----
+    mbar_wait(fullU, (uint32_t)(it & 1));
+    const int wrows = min(32, rows - warp * 32);
+    for (int r = 0; r < wrows; r += 4) {
+      float u[4][KC], dv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        dv[i] = __shfl_sync(CODA_FULL, dl, (r + i) & 31);
+        const float* urow = Ut + (size_t)(warp * 32 + min(r + i, wrows - 1)) * C;
+#pragma unroll
+        for (int k = 0; k < KC; ++k) {
+          const int c = lane + 32 * k;
+          u[i][k] = c < C ? urow[c] : 0.f;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (r + i >= wrows) break;
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < KC; ++k) {
+          const int c = lane + 32 * k;
+          if (c == t) {
+            u[i][k] += dv[i];
+            U[(size_t)(n0 + warp * 32 + r + i) * C + c] = u[i][k];
+          }
+          s += u[i][k];
+        }
+        s = warp_sum(s);
+        if (!isfinite(s)) bad |= CODA_B200_FLAG_NONFINITE_PI;
+        const float den = fmaxf(s, 1e-12f);                             // coda.py:230 clamp_(min=1e-12)
+#pragma unroll
+        for (int k = 0; k < KC; ++k) racc[k] += to_fx(u[i][k] / den, fxs);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(emptyU);
+  }
+  long long* wacc = wacc_all + (size_t)warp * C;
+#pragma unroll
+  for (int k = 0; k < KC; ++k) {
+    const int c = lane + 32 * k;
+    if (c < C) wacc[c] = racc[k];
+  }
+  // consumer-only barrier (the producer warps have left): named barrier 1
+  asm volatile("bar.sync 1, %0;" ::"r"(nwarp_act * 32) : "memory");
+  for (int c = tid; c < C; c += nwarp_act * 32) {
+    long long s2 = 0;
+    for (int w = 0; w < nwarp_act; ++w) s2 += wacc_all[(size_t)w * C + c];
+    if (s2) atomicAdd(pisum_fx + c, (unsigned long long)s2);
+  }
+  if (bad) atomicOr(flags, bad);
+}
+
+static int r1x_tile_rows(int C) {     // rows per tile: U tile <= ~104 KB, multiple of 32, <= 256
+  int tr = (int)((104 * 1024) / ((size_t)C * 4)) / 32 * 32;
+  if (tr > 256) tr = 256;
+  return tr;
+}
+
 extern "C" int coda_b200_pi_rank1(const float* preds, const float* ens, int H, int64_t N, int C, const int64_t* sel,
                                   double lr, int fx_shift, const int32_t* terms /*[2 + 8H]*/, float* U,
                                   int64_t* pisum_fx, uint32_t* flags, int ctas_per_sm, coda_stream_t stream) {
@@ -720,8 +1006,58 @@ extern "C" int coda_b200_pi_rank1(const float* preds, const float* ens, int H, i
   const int32_t* hdr = terms;                                                  // 2 ints
   const R1Term* tlist = reinterpret_cast<const R1Term*>(terms + 2);            // <= 2H x 16 bytes
   cudaStream_t st = as_stream(stream);
+  // bulk-TMA pipeline: C <= 128, 16-byte aligned U / preds / E, item counts that keep every bulk copy aligned
+  // variants (identical bits): "v4" four items per lane (default for C <= 128), "tma" the bulk-TMA pipeline
+  // (measured slower: 8 consumer warps per SM in lock-step phases), "v1" one item per lane (any C)
+  const char* r1env = getenv("CODA_B200_R1");
+  const bool want_tma = r1env && r1env[0] == 't';
+  const bool want_v1 = r1env && r1env[0] == 'v' && r1env[1] == '1';
+  const bool no_tma = !want_tma;
+  const int TR = C <= 128 ? r1x_tile_rows(C) : 0;
+  if (!no_tma && TR >= 32 && (reinterpret_cast<uintptr_t>(U) & 15) == 0) {
+    const size_t u_bytes = ((size_t)TR * C * 4 + 127) & ~(size_t)127;
+    const size_t smem_x = u_bytes + (size_t)R1X_ST * R1X_TB * TR * 4 + (size_t)2 * H * sizeof(R1Term) + (size_t)8 * C * 8 +
+                          (size_t)2 * H * 4 + 8 + (2 + 2 * R1X_ST) * 8;
+    if (smem_x <= 220 * 1024) {
+      long long tiles = (N + TR - 1) / TR;
+      int cap = coda_sm_count();
+      if (ctas_per_sm >= 1 && ctas_per_sm < 8) cap = cap - cap / 8;   // a concurrent stream keeps a few SMs
+      int gridx = (int)min(tiles, (long long)cap);
+#define LAUNCH_R1X(KC)                                                                                              \
+  do {                                                                                                              \
+    CODA_CUDA_OK(cudaFuncSetAttribute(k_pi_rank1_tma<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_x)); \
+    k_pi_rank1_tma<KC><<<gridx, R1X_THREADS, smem_x, st>>>(preds, ens, N, C, TR, reinterpret_cast<const long long*>(sel), \
+                                                          hdr, tlist, (float)lr, exp2f((float)fx_shift), U,        \
+                                                          reinterpret_cast<unsigned long long*>(pisum_fx), flags); \
+  } while (0)
+      if (C <= 32) LAUNCH_R1X(1);
+      else if (C <= 64) LAUNCH_R1X(2);
+      else LAUNCH_R1X(4);
+#undef LAUNCH_R1X
+      CODA_LAUNCH_OK("k_pi_rank1_tma");
+      return CODA_B200_OK;
+    }
+  }
   size_t smem = (size_t)8 * C * 8 + (size_t)2 * H * sizeof(R1Term);
   CODA_CHECK_ARG(smem <= 200 * 1024, "pi_rank1: C=%d too large", C);
+  if (!want_v1 && C <= 128) {
+    long long want4 = (N + 8 * R1V_WI - 1) / (8 * R1V_WI);
+    int cps = (ctas_per_sm < 1 || ctas_per_sm > 8) ? 8 : ctas_per_sm;
+    int grid4 = (int)min(want4, (long long)coda_sm_count() * cps);
+#define LAUNCH_R1V(KC)                                                                                            \
+  do {                                                                                                            \
+    CODA_CUDA_OK(cudaFuncSetAttribute(k_pi_rank1_v4<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    k_pi_rank1_v4<KC><<<grid4, 256, smem, st>>>(preds, ens, N, C, reinterpret_cast<const long long*>(sel), hdr,   \
+                                               tlist, (float)lr, exp2f((float)fx_shift), U,                       \
+                                               reinterpret_cast<unsigned long long*>(pisum_fx), flags);           \
+  } while (0)
+    if (C <= 32) LAUNCH_R1V(1);
+    else if (C <= 64) LAUNCH_R1V(2);
+    else LAUNCH_R1V(4);
+#undef LAUNCH_R1V
+    CODA_LAUNCH_OK("k_pi_rank1_v4");
+    return CODA_B200_OK;
+  }
   long long want = (N + R1_TN - 1) / R1_TN;
   if (ctas_per_sm < 1 || ctas_per_sm > 8) ctas_per_sm = 8;
   int grid = (int)min(want, (long long)coda_sm_count() * ctas_per_sm);

@@ -20,7 +20,7 @@ Two ways to form a group:
 """
 from __future__ import annotations
 
-import ctypes as C
+import ctypes as ct
 
 import torch
 
@@ -91,23 +91,24 @@ class Mailbox:
         self.device = torch.device(device)
         self.dims = (int(world), int(H), int(C), int(rep_words))
         self.bytes = int(self.lib.coda_b200_xchg_box_bytes(*self.dims))
-        ptr = C.c_void_p()
+        ptr = ct.c_void_p()
         with torch.cuda.device(self.device):
-            nat.check(self.lib.coda_b200_xchg_alloc(self.bytes, C.byref(ptr)), "xchg_alloc")
+            nat.check(self.lib.coda_b200_xchg_alloc(self.bytes, ct.byref(ptr)), "xchg_alloc")
         self.ptr = int(ptr.value)
         self.epoch = torch.zeros(4, dtype=torch.int64, device=self.device)
+        torch.cuda.synchronize(self.device)     # the zero fill ran on the current stream; shards may use their own
         self.opened = []
 
     def export(self) -> bytes:
-        buf = C.create_string_buffer(64)
+        buf = ct.create_string_buffer(64)
         with torch.cuda.device(self.device):
             nat.check(self.lib.coda_b200_ipc_export(self.ptr, buf), "ipc_export")
         return buf.raw
 
     def open_peer(self, handle: bytes) -> int:
-        out = C.c_void_p()
+        out = ct.c_void_p()
         with torch.cuda.device(self.device):
-            nat.check(self.lib.coda_b200_ipc_open(C.create_string_buffer(handle, 64), C.byref(out)), "ipc_open")
+            nat.check(self.lib.coda_b200_ipc_open(ct.create_string_buffer(handle, 64), ct.byref(out)), "ipc_open")
         self.opened.append(int(out.value))
         return int(out.value)
 

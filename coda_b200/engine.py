@@ -166,7 +166,8 @@ class Engine:
         self.labeled = self._z((N,), torch.uint8)
         self.conf_fx = self._z((H, C, C), torch.int64)
         self.D = self._e((H, C, C), torch.float32)
-        self.U = self._e((N, C), torch.float32)
+        # 16 bytes of slack behind U: the bulk-TMA marginal refresh rounds the last tile's copy up to 16 bytes
+        self.U = self._e((N * C + 4,), torch.float32)[: N * C].view(N, C)
         self.pisum = self._z((C,), torch.int64)               # THIS shard's column sums (summed over shards in step_mixture)
         self.grid = torch.linspace(1e-6, 1 - 1e-6, P).to(self.dev)   # coda.py:86, built on the host (trap T1)
         self.dL = self._e((C, H, P), torch.float32)
@@ -323,12 +324,15 @@ class Engine:
         self.ent_cls = self._e((max(1, n_ent),), torch.int16)
         self.zmask = self._e((self.npairs, W), torch.int32)
         self.row_of = self._e((self.npairs,), torch.int32)
+        self.row_cls = self._e((max(1, self.n_heavy),), torch.int16)
         cursor = self._z((C,), torch.int32)
         self._call("coda_b200_pair_fill", _ptr(self.hard), H, N, C, _ptr(self.ent_off), _ptr(self.heavy_off),
                    _ptr(self.cls_base), _ptr(cursor), _ptr(self.ent_row), _ptr(self.ent_cls), _ptr(self.zmask),
-                   _ptr(self.row_of), s, n=2)
-        # gains: template rows always; heavy rows only when nothing is cached (recompute modes)
-        self.gain = self._z((T if self.mode == "incremental" else self.npairs,), torch.float32)
+                   _ptr(self.row_of), _ptr(self.row_cls), s, n=2)
+        self.gain = self._z((self.npairs,), torch.float32)      # information gain of every row (templates first)
+        # CODA_B200_FUSED_SCORE=1: one kernel computes the row gains and assembles the per-item EIG (measured slower
+        # than the streaming row-gain kernel followed by the 8-lane assembly)
+        self.fused_score = os.environ.get("CODA_B200_FUSED_SCORE", "0") == "1"
         self.ph_cache = None
         if self.mode == "incremental":
             need = self.npairs * self.Hp * 4
@@ -339,7 +343,6 @@ class Engine:
                 warnings.warn(f"coda_b200: row cache of {need / 2 ** 30:.1f} GiB does not fit "
                               f"({free / 2 ** 30:.1f} GiB free); falling back to mode='recompute'")
                 self.mode = "recompute"
-                self.gain = self._z((self.npairs,), torch.float32)
             else:
                 self.ph_cache = self._e((self.npairs, self.Hp), torch.float32)
 
@@ -416,15 +419,19 @@ class Engine:
                 self.pending = False
             self._call("coda_b200_template_gains", _ptr(self.ph_cache), self.H, self.C, _ptr(self.PB), _ptr(self.m0),
                        _ptr(self.pi_hat), _ptr(self.gain), self._s())
+            if not self.fused_score:
+                self._call("coda_b200_row_gains", _ptr(self.ph_cache), _ptr(self.row_cls), self.n_heavy, self.H, self.C,
+                           _ptr(self.PB), _ptr(self.m0), _ptr(self.pi_hat), _ptr(self.gain), self._s())
         else:
             if self.pending:
                 self._cur().wait_event(self.ev_join)
                 self.pending = False
             self._pair_rows(0, self.ntiles)
         self._call("coda_b200_gain_eig", _ptr(self.U), self.N, self.C, self.H, _ptr(self.ent_off), _ptr(self.heavy_off),
-                   _ptr(self.ent_row), _ptr(self.ent_cls), _ptr(self.ph_cache), _ptr(self.gain), _ptr(self.PB),
-                   _ptr(self.m0), _ptr(self.pi_hat), _ptr(self.labeled), _ptr(self.disagree), self.n_offset,
-                   _ptr(self.eig), _ptr(self.partials), _ptr(self.flags), self._s())
+                   _ptr(self.ent_row), _ptr(self.ent_cls), _ptr(self.ph_cache) if self.fused_score else None,
+                   _ptr(self.gain), _ptr(self.PB), _ptr(self.m0), _ptr(self.pi_hat), _ptr(self.labeled),
+                   _ptr(self.disagree), self.n_offset, self.max_entries, _ptr(self.eig), _ptr(self.partials),
+                   _ptr(self.flags), self._s())
         self.scored = True
 
     def _post_label(self):

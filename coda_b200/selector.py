@@ -124,6 +124,8 @@ class CODA(ModelSelector):
             if d != home:
                 view = view.to(torch.device("cuda", d)).contiguous()
             out.append((view, lo))
+        for d in devs:                                      # the peer copies ran on the current streams; the shards use their own
+            torch.cuda.synchronize(d)
         return out
 
     @classmethod
@@ -322,6 +324,8 @@ class CODA(ModelSelector):
             for e in self.engines:
                 if e.dev not in per_dev:
                     per_dev[e.dev] = labels.to(e.dev, torch.int64).contiguous()
+            for d in per_dev:
+                torch.cuda.synchronize(d)
             self._labels_dev = cache = (labels, per_dev)
         per_dev = cache[1]
         if k <= 0:

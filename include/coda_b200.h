@@ -130,7 +130,8 @@ int coda_b200_shadow_build(const float* preds, int64_t model_stride, int H, int6
  * ensemble sums E the sum over models is taken as E[n][t'] + corrections for the models that disagree with the
  * majority class t' of jvec (exact algebra, fewer gathers); models with a shadow slot are read from the shadow.
  * pisum_fx was zeroed by the step kernel and is accumulated into (this shard's sums).  ctas_per_sm (1..8)
- * bounds the grid so a concurrent stream keeps SM resources. */
+ * bounds the grid so a concurrent stream keeps SM resources.  U must be 16-byte aligned and followed by 16
+ * readable bytes (C <= 128 takes a bulk-TMA pipeline that rounds the last tile's copy up). */
 int coda_b200_pi_rank1(const float* preds, const float* ens, int H, int64_t N, int C, const int64_t* sel, double lr,
                        int fx_shift, const int32_t* terms, float* U, int64_t* pisum_fx, uint32_t* flags,
                        int ctas_per_sm, coda_stream_t stream);
@@ -157,7 +158,8 @@ int coda_b200_pair_count(const uint16_t* hard, int H, int64_t N, int C, int32_t*
 int coda_b200_pair_fill(const uint16_t* hard, int H, int64_t N, int C, const int32_t* ent_off /*[N+1]*/,
                         const int32_t* heavy_off /*[N+1]*/, const int64_t* cls_base /*[C+1]*/,
                         int32_t* cls_cursor /*[C] zeroed*/, int32_t* ent_row, uint16_t* ent_cls,
-                        uint32_t* zmask /*[npairs][Hp/32]*/, int32_t* row_of /*[npairs]*/, coda_stream_t stream);
+                        uint32_t* zmask /*[npairs][Hp/32]*/, int32_t* row_of /*[npairs]*/,
+                        uint16_t* row_cls /*[n_heavy] class of every heavy row*/, coda_stream_t stream);
 /* tiles [ntiles][4] int32 = {class, first work-list position, count <= 32, 0}; processes tiles [tile_lo, tile_hi).
  * Writes gain[row] = H_before - H_after (coda.py:274-276) and, if ph_cache != NULL, the normalised
  * P(best | hypothetical) row (coda.py:271-273), row = row_of[position].  With sel != NULL the launch covers
@@ -183,11 +185,17 @@ int coda_b200_template_gains(const float* ph_cache, int H, int C, const float* P
  * eig[n] = sum_c pi_hat_xi[n][c] * gain(n, c)  (== H_before - sum_c xi * H_after because sum_c xi = 1), the
  * candidate arg-max (first index wins) and runner-up value per block -> partials [blocks][REC_WORDS]. */
 int coda_b200_eig_blocks(int64_t N, int H, int C); /* number of partial records gain_eig writes */
+/* max_entries: the longest entry list (or -1 if unknown); short lists and C <= 128 take an 8-lanes-per-item kernel. */
 int coda_b200_gain_eig(const float* U, int64_t N, int C, int H, const int32_t* ent_off, const int32_t* heavy_off,
                        const int32_t* ent_row, const uint16_t* ent_cls, const float* ph_cache, const float* gain,
                        const float* PB, const float* m0, const float* pi_hat, const uint8_t* labeled,
-                       const uint8_t* disagree, int64_t n_offset, float* eig, int64_t* partials, uint32_t* flags,
-                       coda_stream_t stream);
+                       const uint8_t* disagree, int64_t n_offset, int max_entries, float* eig, int64_t* partials,
+                       uint32_t* flags, coda_stream_t stream);
+/* gain[T + r] (coda.py:274-276) of the n_heavy heavy rows from their cached rows (ph_cache + T*Hp...), row_cls[r] =
+ * class of heavy row r: the HBM-bound stream of the two-kernel scoring pass (row_gains, then gain_eig with
+ * ph_cache == NULL).  Item-major rows make the per-item gains contiguous for the assembly that follows. */
+int coda_b200_row_gains(const float* ph_cache, const uint16_t* row_cls, int64_t n_heavy, int H, int C,
+                        const float* PB, const float* m0, const float* pi_hat, float* gain, coda_stream_t stream);
 
 /* ---- fused single-CTA step kernels: selection, label, posterior update, mixture --------------------------- */
 typedef struct coda_step { /* host struct: this shard's device state */

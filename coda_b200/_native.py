@@ -48,7 +48,7 @@ class StepStruct(C.Structure):
         ("H", i32), ("C", i32), ("N", i64), ("n_offset", i64), ("fx_shift", i32), ("lr", f32),
         ("hard", p), ("labeled", p), ("D", p), ("jvec", p), ("sel", p),
         ("terms", p), ("slot_of_model", p), ("shadow_off", i64), ("shadow_col_stride", i64), ("model_stride", i64),
-        ("have_ens", i32),
+        ("have_ens", i32), ("compact_k", i32),
         ("pisum_fx", p), ("PB", p), ("pi_hat", p), ("m0", p), ("h_before", p), ("best_model", p),
         ("partials", p), ("nblocks", i32), ("eig", p), ("bestrec", p),
         ("labels_global", p), ("hist_idx", p), ("hist_q", p), ("hist_tie", p), ("hist_cap", i64), ("step_ctr", p),
@@ -75,7 +75,11 @@ SIGNATURES = {
     "coda_b200_scan_slab": (i32, [p, i64, i32, i64, i32, p, p, p, p, p, p]),
     "coda_b200_confusion_accum": (i32, [p, i64, p, i32, i64, i32, i32, p, p]),
     "coda_b200_confusion_sorted": (i32, [p, i64, p, p, i32, i64, i32, i32, p, p]),
-    "coda_b200_init_dirichlets": (i32, [p, i32, i32, i32, f64, f64, i32, p, p]),
+    "coda_b200_init_dirichlets": (i32, [p, p, i32, i32, i32, f64, f64, i32, p, p]),
+    "coda_b200_scan_compact": (i32, [p, p, i64, i32, i64, i32, i32, p, p, p, p, p, p]),
+    "coda_b200_confusion_compact": (i32, [p, p, i64, p, i32, i64, i32, i32, i32, p, p, p]),
+    "coda_b200_pi_full_compact": (i32, [p, p, i64, p, i32, i64, i32, i32, p, p, p, p]),
+    "coda_b200_pi_rank1_compact": (i32, [p, p, i64, p, i32, i64, i32, i32, p, f64, i32, p, p, p, p, p]),
     "coda_b200_pi_full": (i32, [p, i64, p, i32, i64, i32, p, p]),
     "coda_b200_pi_reduce": (i32, [p, i64, i32, i32, p, p, p, p]),
     "coda_b200_shadow_build": (i32, [p, i64, i32, i64, i32, p, i32, i64, p, p]),
@@ -88,7 +92,8 @@ SIGNATURES = {
     "coda_b200_pair_rows_tc": (i32, [p, i32, i32, p, p, p, p, p, p, p, i32, p, p, p, p, p, p]),
     "coda_b200_template_gains": (i32, [p, i32, i32, p, p, p, p, p]),
     "coda_b200_eig_blocks": (i32, [i64, i32, i32]),
-    "coda_b200_gain_eig": (i32, [p, i64, i32, i32, p, p, p, p, p, p, p, p, p, p, p, i64, i32, p, p, p, p]),
+    "coda_b200_gain_eig": (i32, [p, i64, i32, i32, p, p, p, p, p, p, p, p, p, p, p, i64, i32, p, p, i32, p, p, p, p]),
+    "coda_b200_ell_build": (i32, [p, p, p, i64, i32, p, p, p]),
     "coda_b200_row_gains": (i32, [p, p, i64, i32, i32, p, p, p, p, p]),
     "coda_b200_step_select": (i32, [PS, PX, p]),
     "coda_b200_step_merge": (i32, [PS, PX, p]),

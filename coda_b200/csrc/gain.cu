@@ -35,6 +35,9 @@ struct GainEigArgs {
   long long* partials;
   uint32_t* flags;
   int pb_smem;
+  const int32_t* ell_row;     // optional ELL copy of the entry lists: [N][ell_k] row ids (-1 = empty) ...
+  const uint16_t* ell_cls;    // ... and classes
+  int ell_k;
 };
 
 __device__ __forceinline__ float gain4(const float4 ph, const float4 pb, const float4 m, const float4 fm, float pic) {
@@ -413,11 +416,13 @@ __global__ void __launch_bounds__(256) k_eig_assemble_g8(GainEigArgs a, int nblo
   for (long long wb = ((long long)blockIdx.x * 8 + warp) * 4 * IT8; wb < a.N; wb += per_iter) {
     const long long nb = wb + grp * IT8;
     int e0[IT8], ne[IT8];
+    if (!a.ell_row) {
 #pragma unroll
-    for (int i = 0; i < IT8; ++i) {
-      const long long n = min(nb + i, a.N - 1);
-      e0[i] = __ldg(a.ent_off + n);
-      ne[i] = __ldg(a.ent_off + n + 1) - e0[i];
+      for (int i = 0; i < IT8; ++i) {
+        const long long n = min(nb + i, a.N - 1);
+        e0[i] = __ldg(a.ent_off + n);
+        ne[i] = __ldg(a.ent_off + n + 1) - e0[i];
+      }
     }
     float u[IT8][KC8];
     int er[IT8][4], ec[IT8][4];
@@ -434,7 +439,12 @@ __global__ void __launch_bounds__(256) k_eig_assemble_g8(GainEigArgs a, int nblo
       for (int j = 0; j < 4; ++j) {
         const int e = g + 8 * j;
         er[i][j] = -1; ec[i][j] = 0;
-        if (e < ne[i]) {
+        if (a.ell_row) {     // the entry address follows from the item index: one dependent load level less
+          if (e < a.ell_k) {
+            er[i][j] = __ldg(a.ell_row + (size_t)n * a.ell_k + e);
+            ec[i][j] = __ldg(a.ell_cls + (size_t)n * a.ell_k + e);
+          }
+        } else if (e < ne[i]) {
           er[i][j] = __ldg(a.ent_row + e0[i] + e);
           ec[i][j] = __ldg(a.ent_cls + e0[i] + e);
         }
@@ -529,8 +539,8 @@ extern "C" int coda_b200_gain_eig(const float* U, int64_t N, int C, int H, const
                                   const int32_t* heavy_off, const int32_t* ent_row, const uint16_t* ent_cls,
                                   const float* ph_cache, const float* gain, const float* PB, const float* m0,
                                   const float* pi_hat, const uint8_t* labeled, const uint8_t* disagree,
-                                  int64_t n_offset, int max_entries, float* eig, int64_t* partials, uint32_t* flags,
-                                  coda_stream_t stream) {
+                                  int64_t n_offset, int max_entries, const int32_t* ell_row, const uint16_t* ell_cls,
+                                  int ell_k, float* eig, int64_t* partials, uint32_t* flags, coda_stream_t stream) {
   CODA_CHECK_ARG(U && ent_off && heavy_off && ent_row && ent_cls && gain && PB && m0 && pi_hat && labeled && disagree &&
                      eig && partials && flags,
                  "gain_eig: null pointer");
@@ -541,6 +551,8 @@ extern "C" int coda_b200_gain_eig(const float* U, int64_t N, int C, int H, const
   a.ph_cache = ph_cache; a.gain = gain; a.PB = PB; a.m0 = m0; a.pi_hat = pi_hat;
   a.labeled = labeled; a.disagree = disagree; a.n_offset = n_offset; a.eig = eig;
   a.partials = reinterpret_cast<long long*>(partials); a.flags = flags;
+  a.ell_row = (ell_row && ell_cls && ell_k >= 1 && ell_k <= 32) ? ell_row : nullptr;
+  a.ell_cls = ell_cls; a.ell_k = ell_k;
   const bool from_cache = ph_cache != nullptr;
   const int nq = !from_cache ? 0 : ((a.Hp == 128) ? 1 : (a.Hp == 256 ? 2 : 0));   // NQ = 0: m0 / f(m0) copies in shared memory
   const int kc = C <= 32 ? 1 : (C <= 64 ? 2 : (C <= 128 ? 4 : 0));
@@ -632,5 +644,28 @@ extern "C" int coda_b200_template_gains(const float* ph_cache, int H, int C, con
   if (grid > cap) grid = cap;
   k_template_gains<<<grid, 256, (size_t)2 * Hp * 4, as_stream(stream)>>>(ph_cache, H, Hp, T, PB, m0, pi_hat, gain);
   CODA_LAUNCH_OK("k_template_gains");
+  return CODA_B200_OK;
+}
+
+// ELL copy of the per-item entry lists for the 8-lane assembly: ell_row[n][k] = row id or -1, ell_cls[n][k] = class.
+__global__ void k_ell_build(const int32_t* __restrict__ ent_off, const int32_t* __restrict__ ent_row,
+                            const uint16_t* __restrict__ ent_cls, long long N, int K, int32_t* __restrict__ ell_row,
+                            uint16_t* __restrict__ ell_cls) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * K) return;
+  const long long n = i / K;
+  const int k = (int)(i % K);
+  const int o = ent_off[n] + k;
+  const bool has = o < ent_off[n + 1];
+  ell_row[i] = has ? ent_row[o] : -1;
+  ell_cls[i] = has ? ent_cls[o] : (uint16_t)0;
+}
+
+extern "C" int coda_b200_ell_build(const int32_t* ent_off, const int32_t* ent_row, const uint16_t* ent_cls, int64_t N,
+                                   int K, int32_t* ell_row, uint16_t* ell_cls, coda_stream_t stream) {
+  CODA_CHECK_ARG(ent_off && ent_row && ent_cls && ell_row && ell_cls && K >= 1 && K <= 32, "ell_build: bad arguments");
+  const long long tot = (long long)N * K;
+  k_ell_build<<<(unsigned)((tot + 255) / 256), 256, 0, as_stream(stream)>>>(ent_off, ent_row, ent_cls, N, K, ell_row, ell_cls);
+  CODA_LAUNCH_OK("k_ell_build");
   return CODA_B200_OK;
 }

@@ -385,7 +385,8 @@ extern "C" int coda_b200_confusion_accum(const float* preds, int64_t model_strid
 // init_dirichlets: D = multiplier * (base + prior_strength * conf / max(rowsum, 1e-6))
 // one warp per (h, c) row.
 // ---------------------------------------------------------------------------------------
-__global__ void k_init_dirichlets(const long long* __restrict__ conf_fx, int H, int C, int shift,
+__global__ void k_init_dirichlets(const long long* __restrict__ conf_fx, const long long* __restrict__ conf_rest,
+                                  int H, int C, int shift,
                                   float prior_strength, float multiplier, int uniform_prior,
                                   float* __restrict__ D) {
   const int lane = threadIdx.x & 31;
@@ -393,25 +394,28 @@ __global__ void k_init_dirichlets(const long long* __restrict__ conf_fx, int H, 
   if (row >= (long long)H * C) return;
   const int c = (int)(row % C);
   const long long* src = conf_fx + row * C;
+  const long long rest = conf_rest ? conf_rest[row] : 0;          // compact slab: carried by every column of the row
   float rs = 0.f;
-  for (int j = lane; j < C; j += 32) rs += (float)from_fx(src[j], shift);
+  for (int j = lane; j < C; j += 32) rs += (float)from_fx(src[j] + rest, shift);
   rs = warp_sum(rs);
   rs = fmaxf(rs, 1e-6f);                                        // coda.py:43 clamp_min(1e-6)
   const float off = uniform_prior ? (float)(2.0 / C) : (float)(1.0 / (C - 1));   // coda.py:53, 57
   for (int j = lane; j < C; j += 32) {
-    float conf = (float)from_fx(src[j], shift) / rs;
+    float conf = (float)from_fx(src[j] + rest, shift) / rs;
     float base = (!uniform_prior && j == c) ? 1.0f : off;       // coda.py:60 fill_diagonal_(1.0)
     D[row * C + j] = multiplier * (base + prior_strength * conf);  // coda.py:63, 196
   }
 }
 
-extern "C" int coda_b200_init_dirichlets(const int64_t* conf_fx, int H, int C, int fx_shift, double prior_strength,
-                                         double multiplier, int uniform_prior, float* D, coda_stream_t stream) {
+extern "C" int coda_b200_init_dirichlets(const int64_t* conf_fx, const int64_t* conf_rest, int H, int C, int fx_shift,
+                                         double prior_strength, double multiplier, int uniform_prior, float* D,
+                                         coda_stream_t stream) {
   CODA_CHECK_ARG(conf_fx && D, "init_dirichlets: null pointer");
   long long rows = (long long)H * C;
   int wpb = 8;
   k_init_dirichlets<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, as_stream(stream)>>>(
-      reinterpret_cast<const long long*>(conf_fx), H, C, fx_shift, (float)prior_strength, (float)multiplier,
+      reinterpret_cast<const long long*>(conf_fx), reinterpret_cast<const long long*>(conf_rest), H, C, fx_shift,
+      (float)prior_strength, (float)multiplier,
       uniform_prior, D);
   CODA_LAUNCH_OK("k_init_dirichlets");
   return CODA_B200_OK;
@@ -1007,11 +1011,12 @@ extern "C" int coda_b200_pi_rank1(const float* preds, const float* ens, int H, i
   const R1Term* tlist = reinterpret_cast<const R1Term*>(terms + 2);            // <= 2H x 16 bytes
   cudaStream_t st = as_stream(stream);
   // bulk-TMA pipeline: C <= 128, 16-byte aligned U / preds / E, item counts that keep every bulk copy aligned
-  // variants (identical bits): "v4" four items per lane (default for C <= 128), "tma" the bulk-TMA pipeline
-  // (measured slower: 8 consumer warps per SM in lock-step phases), "v1" one item per lane (any C)
+  // variants (identical bits): "v1" one item per lane (default; measured fastest: 0.40 ms at cfg3), "v4" four items
+  // per lane / 512-byte runs per term (0.51 ms), "tma" the bulk-TMA pipeline (1.2 ms: 8 consumer warps per SM in
+  // lock-step phases).  CODA_B200_R1 selects one for A/B runs.
   const char* r1env = getenv("CODA_B200_R1");
   const bool want_tma = r1env && r1env[0] == 't';
-  const bool want_v1 = r1env && r1env[0] == 'v' && r1env[1] == '1';
+  const bool want_v1 = !(r1env && r1env[0] == 'v' && r1env[1] == '4');
   const bool no_tma = !want_tma;
   const int TR = C <= 128 ? r1x_tile_rows(C) : 0;
   if (!no_tma && TR >= 32 && (reinterpret_cast<uintptr_t>(U) & 15) == 0) {

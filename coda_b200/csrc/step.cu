@@ -65,7 +65,11 @@ __device__ void apply_label(const coda_step_t& a, int t, const int* jv, int* cnt
     int off = carry;
     for (int w = 0; w < warp; ++w) off += wtot[w];
     const int k = off + incl - n;
-    if (n) {
+    if (n && a.compact_k > 0) {
+      // compact slab: a term names (model, class); pi_rank1_compact resolves it by a K-way match
+      terms[k] = R1Term{(long long)h, 1.f, j};
+      if (n == 2) terms[k + 1] = R1Term{(long long)h, -1.f, tp};
+    } else if (n) {
       const int slot = a.slot_of_model ? a.slot_of_model[h] : -1;
       // shadow: [slot][class][col_stride] (item stride 1); reference layout: [model][item][class] (item stride C)
       const long long base = slot >= 0 ? a.shadow_off + (long long)slot * C * a.shadow_col_stride : (long long)h * a.model_stride;

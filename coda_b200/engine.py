@@ -47,19 +47,26 @@ class Engine:
     def __init__(self, preds: torch.Tensor, *, alpha: float, learning_rate: float, multiplier: float,
                  uniform_prior: bool, hyp_w: float = 1.0, mode: str = "incremental", n_offset: int = 0,
                  n_global: int | None = None, world: int = 1, own_stream: bool = False):
+        from .datasets import CompactSlab
         if mode not in MODES:
             raise ValueError(f"mode must be one of {MODES}")
-        if not (isinstance(preds, torch.Tensor) and preds.is_cuda):
+        self.compact = preds if isinstance(preds, CompactSlab) else None
+        if not ((isinstance(preds, torch.Tensor) or self.compact is not None) and preds.is_cuda):
             raise RuntimeError("coda_b200: dataset.preds must live on a CUDA (sm_100a) device; "
                                "there is no CPU path in this package")
-        if preds.dtype != torch.float32 or preds.dim() != 3:
-            raise TypeError("coda_b200: preds must be a float32 (H, N, C) tensor (coda/datasets.py:14)")
         H, N, Cc = (int(s) for s in preds.shape)
         if N < 1:
             raise ValueError("coda_b200: empty shard (fewer items than shards?)")
-        if not (preds.stride(2) == 1 and preds.stride(1) == Cc and (H == 1 or preds.stride(0) >= N * Cc)):
-            raise ValueError("coda_b200: preds must be (H, N, C) with contiguous items (an N-range view of a "
-                             "contiguous slab is fine)")
+        if self.compact is not None:
+            if mode == "recompute_all":
+                raise NotImplementedError("coda_b200: mode='recompute_all' is not offered for a compact slab")
+            self.K = self.compact.K
+        else:
+            if preds.dtype != torch.float32 or preds.dim() != 3:
+                raise TypeError("coda_b200: preds must be a float32 (H, N, C) tensor (coda/datasets.py:14)")
+            if not (preds.stride(2) == 1 and preds.stride(1) == Cc and (H == 1 or preds.stride(0) >= N * Cc)):
+                raise ValueError("coda_b200: preds must be (H, N, C) with contiguous items (an N-range view of a "
+                                 "contiguous slab is fine)")
         self.lib = nat.load()
         self.preds = preds
         self.dev = preds.device
@@ -69,7 +76,10 @@ class Engine:
             # traffic; streaming kernels measured the same at 64 and 128).  A per-device limit.
             nat.check(self.lib.coda_b200_set_l2_fetch_granularity(int(os.environ.get("CODA_B200_L2_FETCH", "64"))), "l2_fetch")
         self.H, self.N, self.C = H, N, Cc
-        self.model_stride = int(preds.stride(0)) if H > 1 else N * Cc
+        if self.compact is not None:
+            self.model_stride = int(self.compact.ids.stride(0)) if H > 1 else N * self.K     # elements of ids / probs
+        else:
+            self.model_stride = int(preds.stride(0)) if H > 1 else N * Cc
         self.Hp = (H + 31) // 32 * 32
         self.W = self.Hp // 32
         self.P = 256
@@ -164,7 +174,10 @@ class Engine:
         self.pseudo = self._e((N,), torch.int32)
         self.disagree = self._e((N,), torch.uint8)
         self.labeled = self._z((N,), torch.uint8)
-        self.conf_fx = self._z((H, C, C), torch.int64)
+        # soft-confusion sums (coda.py:42), int64 fixed point; the compact slab adds one "every column" term per row
+        self.conf_buf = self._z((H * C * C + H * C,), torch.int64)
+        self.conf_fx = self.conf_buf[: H * C * C].view(H, C, C)
+        self.conf_rest = self.conf_buf[H * C * C:].view(H, C) if self.compact is not None else None
         self.D = self._e((H, C, C), torch.float32)
         # 16 bytes of slack behind U: the bulk-TMA marginal refresh rounds the last tile's copy up to 16 bytes
         self.U = self._e((N * C + 4,), torch.float32)[: N * C].view(N, C)
@@ -206,7 +219,7 @@ class Engine:
         self.hist_q = self._z((HIST_CAP,), torch.float32)
         self.hist_tie = self._z((HIST_CAP,), torch.int32)
         # ensemble sums E[n][c] (N*C floats) feed pi_rank1's majority shortcut; CODA_B200_ENS=0 disables it
-        self.ens = self._e((N, C), torch.float32) if os.environ.get("CODA_B200_ENS", "1") != "0" else None
+        self.ens = self._e((N, C), torch.float32) if (os.environ.get("CODA_B200_ENS", "1") != "0" or self.compact is not None) else None
         cls_per_batch = max(1, min(C, TABLE_BATCH_BYTES // max(1, self.lib.coda_b200_tables_scratch_bytes(H, 1))))
         self.table_batch = int(cls_per_batch)
         self.scratch = self._e((int(self.lib.coda_b200_tables_scratch_bytes(H, self.table_batch)),), torch.uint8)
@@ -217,10 +230,11 @@ class Engine:
         st.hard, st.labeled, st.D, st.jvec, st.sel = _ptr(self.hard), _ptr(self.labeled), _ptr(self.D), _ptr(self.jvec), _ptr(self.sel)
         st.terms = _ptr(self.terms)
         st.slot_of_model = _ptr(self.slot_of_model)
-        st.shadow_off = ((self.shadow.data_ptr() - self.preds.data_ptr()) // 4) if self.shadow is not None else 0
+        st.shadow_off = ((self.shadow.data_ptr() - self._slab_ptr()) // 4) if self.shadow is not None else 0
         st.shadow_col_stride = self.shadow_cs
         st.model_stride = self.model_stride
         st.have_ens = 1 if self.ens is not None else 0
+        st.compact_k = self.K if self.compact is not None else 0
         st.pisum_fx, st.PB, st.pi_hat, st.m0 = _ptr(self.pisum), _ptr(self.PB), _ptr(self.pi_hat), _ptr(self.m0)
         st.h_before, st.best_model = _ptr(self.hb), _ptr(self.best_model)
         st.partials, st.nblocks, st.eig, st.bestrec = _ptr(self.partials), self.nblocks, _ptr(self.eig), _ptr(self.bestrec)
@@ -230,6 +244,9 @@ class Engine:
         st.flags = _ptr(self.flags)
         self.st = st
 
+    def _slab_ptr(self):
+        return self.preds.data_ptr() if self.compact is None else 0
+
     def _x(self):
         return self.xchg if (self.xchg is not None and self.world > 1) else None
 
@@ -238,6 +255,13 @@ class Engine:
     def construct_scan(self):
         with self._on():
             H, N, C, s = self.H, self.N, self.C, self._s()
+            if self.compact is not None:
+                cs = self.compact
+                self._call("coda_b200_scan_compact", _ptr(cs.ids), _ptr(cs.probs), self.model_stride, H, N, C, self.K,
+                           _ptr(self.hard), _ptr(self.pseudo), _ptr(self.disagree), _ptr(self.ens), _ptr(self.flags), s)
+                self._call("coda_b200_confusion_compact", _ptr(cs.ids), _ptr(cs.probs), self.model_stride,
+                           _ptr(self.pseudo), H, N, C, self.K, self.fx_shift, _ptr(self.conf_fx), _ptr(self.conf_rest), s)
+                return
             self._call("coda_b200_scan_slab", _ptr(self.preds), self.model_stride, H, N, C, _ptr(self.hard),
                        _ptr(self.pseudo), _ptr(self.disagree), _ptr(self.ens), _ptr(self.flags), s)
             if C <= 128:
@@ -252,9 +276,9 @@ class Engine:
     def construct_posterior(self):
         with self._on():
             H, C, s = self.H, self.C, self._s()
-            self._call("coda_b200_init_dirichlets", _ptr(self.conf_fx), H, C, self.fx_shift, self.prior_strength,
-                       self.multiplier, int(self.uniform_prior), _ptr(self.D), s)
-            self.conf_fx = None                                     # H*C*C int64, only needed once
+            self._call("coda_b200_init_dirichlets", _ptr(self.conf_fx), _ptr(self.conf_rest), H, C, self.fx_shift,
+                       self.prior_strength, self.multiplier, int(self.uniform_prior), _ptr(self.D), s)
+            self.conf_fx = self.conf_rest = self.conf_buf = None    # H*C*C int64, only needed once
             self._marginals_full()
             self._build_rows()
             self._build_shadow()
@@ -276,7 +300,15 @@ class Engine:
     def _marginals_full(self):
         """coda.py:226-233 as one streaming pass; leaves THIS shard's column sums in ``pisum``."""
         H, N, C, s = self.H, self.N, self.C, self._s()
-        self._call("coda_b200_pi_full", _ptr(self.preds), self.model_stride, _ptr(self.D), H, N, C, _ptr(self.U), s)
+        if self.compact is not None:
+            cs = self.compact
+            dt = self._e((H, C, C), torch.float32)                  # D transposed + row sums: construction-time scratch
+            rs = self._e((H, C), torch.float32)
+            self._call("coda_b200_pi_full_compact", _ptr(cs.ids), _ptr(cs.probs), self.model_stride, _ptr(self.D), H, N, C,
+                       self.K, _ptr(dt), _ptr(rs), _ptr(self.U), s, n=3)
+            del dt, rs
+        else:
+            self._call("coda_b200_pi_full", _ptr(self.preds), self.model_stride, _ptr(self.D), H, N, C, _ptr(self.U), s)
         self._call("coda_b200_pi_reduce", _ptr(self.U), N, C, self.fx_shift, None, _ptr(self.pisum),
                    _ptr(self.flags), s)
 
@@ -329,6 +361,14 @@ class Engine:
         self._call("coda_b200_pair_fill", _ptr(self.hard), H, N, C, _ptr(self.ent_off), _ptr(self.heavy_off),
                    _ptr(self.cls_base), _ptr(cursor), _ptr(self.ent_row), _ptr(self.ent_cls), _ptr(self.zmask),
                    _ptr(self.row_of), _ptr(self.row_cls), s, n=2)
+        # ELL copy of the entry lists when the longest one fits four entries per lane of an 8-lane group
+        self.ell_row, self.ell_cls, self.ell_k = None, None, 0
+        if 0 < self.max_entries <= 32 and C <= 128:
+            self.ell_k = (self.max_entries + 3) // 4 * 4
+            self.ell_row = self._e((N, self.ell_k), torch.int32)
+            self.ell_cls = self._e((N, self.ell_k), torch.int16)
+            self._call("coda_b200_ell_build", _ptr(self.ent_off), _ptr(self.ent_row), _ptr(self.ent_cls), N, self.ell_k,
+                       _ptr(self.ell_row), _ptr(self.ell_cls), s)
         self.gain = self._z((self.npairs,), torch.float32)      # information gain of every row (templates first)
         # CODA_B200_FUSED_SCORE=1: one kernel computes the row gains and assembles the per-item EIG (measured slower
         # than the streaming row-gain kernel followed by the 8-lane assembly)
@@ -349,7 +389,7 @@ class Engine:
     def _build_shadow(self):
         """Class-major shadow copy of as many models as spare HBM allows (least accurate first)."""
         self.shadow, self.slot_of_model, self.n_shadow, self.shadow_cs = None, None, 0, 0
-        if self.mode == "recompute_all" or os.environ.get("CODA_B200_SHADOW", "1") == "0":
+        if self.mode == "recompute_all" or os.environ.get("CODA_B200_SHADOW", "1") == "0" or self.compact is not None:
             return
         H, N, C = self.H, self.N, self.C
         cs = (N + 3) // 4 * 4                                   # every (slot, class) column starts 16-byte aligned
@@ -430,8 +470,8 @@ class Engine:
         self._call("coda_b200_gain_eig", _ptr(self.U), self.N, self.C, self.H, _ptr(self.ent_off), _ptr(self.heavy_off),
                    _ptr(self.ent_row), _ptr(self.ent_cls), _ptr(self.ph_cache) if self.fused_score else None,
                    _ptr(self.gain), _ptr(self.PB), _ptr(self.m0), _ptr(self.pi_hat), _ptr(self.labeled),
-                   _ptr(self.disagree), self.n_offset, self.max_entries, _ptr(self.eig), _ptr(self.partials),
-                   _ptr(self.flags), self._s())
+                   _ptr(self.disagree), self.n_offset, self.max_entries, _ptr(self.ell_row), _ptr(self.ell_cls),
+                   self.ell_k, _ptr(self.eig), _ptr(self.partials), _ptr(self.flags), self._s())
         self.scored = True
 
     def _post_label(self):
@@ -465,9 +505,15 @@ class Engine:
                 self._pair_rows(0, self.max_cls_tiles, gains=False, sel=True)
             if fork:
                 self.ev_join.record(self.side)
-        self._call("coda_b200_pi_rank1", _ptr(self.preds), _ptr(self.ens), H, N, C, _ptr(self.sel), self.lr,
-                   self.fx_shift, _ptr(self.terms), _ptr(self.U), _ptr(self.pisum), _ptr(self.flags),
-                   4 if fork else 8, s)
+        if self.compact is not None:
+            cs = self.compact
+            self._call("coda_b200_pi_rank1_compact", _ptr(cs.ids), _ptr(cs.probs), self.model_stride, _ptr(self.ens), H, N,
+                       C, self.K, _ptr(self.sel), self.lr, self.fx_shift, _ptr(self.terms), _ptr(self.U),
+                       _ptr(self.pisum), _ptr(self.flags), s)
+        else:
+            self._call("coda_b200_pi_rank1", _ptr(self.preds), _ptr(self.ens), H, N, C, _ptr(self.sel), self.lr,
+                       self.fx_shift, _ptr(self.terms), _ptr(self.U), _ptr(self.pisum), _ptr(self.flags),
+                       4 if fork else 8, s)
         if fork:
             main.wait_event(self.ev_tables)     # the mixture needs PB[t]; the rows are awaited by the scoring pass
             self.pending = True
@@ -712,7 +758,7 @@ def build_engines(shards, group, **kw):
     for e in engines:
         e.construct_scan()
     group.attach(engines)
-    group.allreduce_sum_([e.conf_fx for e in engines])          # coda.py:42 sums over ALL items
+    group.allreduce_sum_([e.conf_buf for e in engines])         # coda.py:42 sums over ALL items
     for e in engines:
         e.construct_posterior()
     for e in engines:

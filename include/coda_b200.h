@@ -104,8 +104,10 @@ int coda_b200_confusion_sorted(const float* preds, int64_t model_stride, const i
                                coda_stream_t stream);
 
 /* Row-normalise (coda.py:43) and build the Dirichlet prior (coda.py:46-63, 196). */
-int coda_b200_init_dirichlets(const int64_t* conf_fx, int H, int C, int fx_shift, double prior_strength,
-                              double multiplier, int uniform_prior, float* D, coda_stream_t stream);
+/* conf_rest (optional, compact slab): [H][C] sums every column of row (h, c) carries in addition (see below). */
+int coda_b200_init_dirichlets(const int64_t* conf_fx, const int64_t* conf_rest, int H, int C, int fx_shift,
+                              double prior_strength, double multiplier, int uniform_prior, float* D,
+                              coda_stream_t stream);
 
 /* ---- consensus marginals (CODA.update_pi_hat, coda.py:226-233) ------------------------ */
 
@@ -135,6 +137,28 @@ int coda_b200_shadow_build(const float* preds, int64_t model_stride, int H, int6
 int coda_b200_pi_rank1(const float* preds, const float* ens, int H, int64_t N, int C, const int64_t* sel, double lr,
                        int fx_shift, const int32_t* terms, float* U, int64_t* pisum_fx, uint32_t* flags,
                        int ctas_per_sm, coda_stream_t stream);
+
+/* ---- compact slab (BASELINE.json configs[4]: M=1024, N=4e6, C=1000 is 16.4 TB dense; no reference counterpart --
+ *      the reference cannot run there, coda.py:227 materialises a second slab) ----------------------------------
+ * For every (h, n) the K <= 8 highest-scoring classes: ids [H][N][K] u16 (descending score) and probs [H][N][K] f32;
+ * every other class gets rest = (1 - sum_j probs) / (C - K).  Models are model_stride ELEMENTS apart in both
+ * arrays.  Each stage below produces what its dense twin produces on the densified slab. */
+int coda_b200_scan_compact(const uint16_t* ids, const float* probs, int64_t model_stride, int H, int64_t N, int C,
+                           int K, uint16_t* hard, int32_t* pseudo, uint8_t* disagree, float* ens_out, uint32_t* flags,
+                           coda_stream_t stream);
+/* coda.py:42: conf[h][y][j] == conf_fx[h][y][j] + conf_rest[h][y] (both ACCUMULATED into, int64 fixed point). */
+int coda_b200_confusion_compact(const uint16_t* ids, const float* probs, int64_t model_stride, const int32_t* pseudo,
+                                int H, int64_t N, int C, int K, int fx_shift, int64_t* conf_fx, int64_t* conf_rest,
+                                coda_stream_t stream);
+/* coda.py:227-229.  DT_scratch [H][C][C] and RS_scratch [H][C] floats are overwritten (D transposed, row sums). */
+int coda_b200_pi_full_compact(const uint16_t* ids, const float* probs, int64_t model_stride, const float* D, int H,
+                              int64_t N, int C, int K, float* DT_scratch, float* RS_scratch, float* U,
+                              coda_stream_t stream);
+/* coda.py:319 (see coda_b200_pi_rank1); the gather list was built with coda_step_t.compact_k = K. */
+int coda_b200_pi_rank1_compact(const uint16_t* ids, const float* probs, int64_t model_stride, const float* ens, int H,
+                               int64_t N, int C, int K, const int64_t* sel, double lr, int fx_shift,
+                               const int32_t* terms, float* U, int64_t* pisum_fx, uint32_t* flags,
+                               coda_stream_t stream);
 
 /* ---- Beta quadrature tables (dirichlet_to_beta coda.py:14-25, compute_pbest_beta_batched
  *      coda.py:77-119, batch_update_beta coda.py:150-168) for classes [cls_lo, cls_hi) ------- */
@@ -185,12 +209,16 @@ int coda_b200_template_gains(const float* ph_cache, int H, int C, const float* P
  * eig[n] = sum_c pi_hat_xi[n][c] * gain(n, c)  (== H_before - sum_c xi * H_after because sum_c xi = 1), the
  * candidate arg-max (first index wins) and runner-up value per block -> partials [blocks][REC_WORDS]. */
 int coda_b200_eig_blocks(int64_t N, int H, int C); /* number of partial records gain_eig writes */
-/* max_entries: the longest entry list (or -1 if unknown); short lists and C <= 128 take an 8-lanes-per-item kernel. */
+/* max_entries: the longest entry list (or -1 if unknown); short lists and C <= 128 take an 8-lanes-per-item kernel,
+ * which reads the lists from the optional ELL copy (coda_b200_ell_build; ell_k = padded list length <= 32). */
 int coda_b200_gain_eig(const float* U, int64_t N, int C, int H, const int32_t* ent_off, const int32_t* heavy_off,
                        const int32_t* ent_row, const uint16_t* ent_cls, const float* ph_cache, const float* gain,
                        const float* PB, const float* m0, const float* pi_hat, const uint8_t* labeled,
-                       const uint8_t* disagree, int64_t n_offset, int max_entries, float* eig, int64_t* partials,
-                       uint32_t* flags, coda_stream_t stream);
+                       const uint8_t* disagree, int64_t n_offset, int max_entries, const int32_t* ell_row,
+                       const uint16_t* ell_cls, int ell_k, float* eig, int64_t* partials, uint32_t* flags,
+                       coda_stream_t stream);
+int coda_b200_ell_build(const int32_t* ent_off, const int32_t* ent_row, const uint16_t* ent_cls, int64_t N, int K,
+                        int32_t* ell_row /*[N][K], -1 = empty*/, uint16_t* ell_cls /*[N][K]*/, coda_stream_t stream);
 /* gain[T + r] (coda.py:274-276) of the n_heavy heavy rows from their cached rows (ph_cache + T*Hp...), row_cls[r] =
  * class of heavy row r: the HBM-bound stream of the two-kernel scoring pass (row_gains, then gain_eig with
  * ph_cache == NULL).  Item-major rows make the per-item gains contiguous for the assembly that follows. */
@@ -213,6 +241,7 @@ typedef struct coda_step { /* host struct: this shard's device state */
   const int32_t* slot_of_model;
   int64_t shadow_off, shadow_col_stride, model_stride;
   int have_ens;
+  int compact_k; /* > 0: the slab is in the compact top-K form, the gather list names (model, class) pairs */
   /* marginals / mixture */
   int64_t* pisum_fx;   /* [C] local sums */
   const float* PB;     /* [C][Hp] */

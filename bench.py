@@ -36,6 +36,10 @@ WORKLOADS = {
     "cfg3": dict(H=256, N=1_000_000, C=100),     # BASELINE.json configs[2] / configs[3]
     "cfg2": dict(H=64, N=50_000, C=10),          # BASELINE.json configs[1] (parity config)
     "mini": dict(H=32, N=20_000, C=10),          # smoke-sized
+    # BASELINE.json configs[4]: 16.4 TB as dense fp32 -- runs from the compact top-K slab (98 GB over 8 GPUs); perf-only,
+    # the reference cannot run it (coda.py:227 materialises a second slab)
+    "cfg5": dict(H=1024, N=4_000_000, C=1000, K=4, compact=True),
+    "cfg5mini": dict(H=1024, N=131_072, C=1000, K=4, compact=True),
 }
 METRIC = "acquisition steps/sec (M=256,N=1e6,C=100)"
 
@@ -138,7 +142,8 @@ def host_cores():
 
 
 def workload_string(args, wl, world):
-    return (f"synthetic M={wl['H']} N={wl['N']} C={wl['C']} ({args.workload}{', dense' if args.dense else ''}), "
+    form = f", compact top-{wl['K']} slab" if wl.get("compact") else ""
+    return (f"synthetic M={wl['H']} N={wl['N']} C={wl['C']} ({args.workload}{', dense' if args.dense else ''}{form}), "
             f"N-axis sharded over {world} GPU(s)")
 
 
@@ -273,7 +278,7 @@ def run_reference(args):
 
 # ---------------------------------------------------------------------------------------------------
 HOT = {   # C-ABI entry point -> kernel name printed in the roofline line
-    "coda_b200_gain_eig": "k_gain_eig", "coda_b200_pi_rank1": "k_pi_rank1", "coda_b200_pair_rows_tc": "k_pair_rows_tc",
+    "coda_b200_row_gains": "k_row_gains", "coda_b200_gain_eig": "k_eig_assemble_g8", "coda_b200_pi_rank1_compact": "k_pi_rank1_compact", "coda_b200_pi_rank1": "k_pi_rank1", "coda_b200_pair_rows_tc": "k_pair_rows_tc",
     "coda_b200_pair_rows": "k_pair_rows", "coda_b200_pi_full": "k_pi_full", "coda_b200_template_gains": "k_template_gains",
     "coda_b200_beta_tables": "k_beta_nodes+k_beta_combine+k_pb_normalize", "coda_b200_step_select": "k_step_select",
     "coda_b200_step_mixture": "k_step_mixture",
@@ -284,10 +289,14 @@ def algorithmic_bytes(eng):
     """Algorithmic bytes per launch, per shard."""
     H, N, C, Hp = eng.H, eng.N, eng.C, eng.Hp
     ent, heavy = eng.n_entries, eng.n_heavy
+    lists = 6 * N * eng.ell_k if eng.ell_row is not None else 6 * ent + 8 * N
     return {
-        # cached rows of the heavy pairs + U rows + entry lists + offsets + template-gain lookups; writes eig
-        "coda_b200_gain_eig": (4 * heavy * Hp if eng.ph_cache is not None else 4 * heavy) + 4 * N * C + 6 * ent + 8 * N
-                              + 4 * (ent - heavy) + 2 * N + 4 * N,
+        # the cached row of every heavy (item, class) + its class id; writes one gain per row
+        "coda_b200_row_gains": 4 * heavy * Hp + 2 * heavy + 4 * heavy,
+        # U rows + entry lists + one gain per entry + candidate masks; writes eig
+        "coda_b200_gain_eig": ((4 * heavy * Hp) if getattr(eng, "fused_score", False) else 0) + 4 * N * C + lists + 4 * ent
+                              + 2 * N + 4 * N,
+        "coda_b200_pi_rank1_compact": 24 * H * N + 4 * N * C + 8 * N,
         # one float per (model, item) + the U row pass (read all, write one column) + the ensemble column
         "coda_b200_pi_rank1": 4 * H * N + 4 * N * C + 4 * N + 4 * N,
         "coda_b200_pi_full": 4 * H * N * C + 4 * N * C,
@@ -352,7 +361,11 @@ def main():
 
     def dataset(dense):
         t = time.time()
-        ds = SyntheticDataset(H, N, C, seed=args.seed, device=dev, dense=dense, rank=rank, world=world)
+        if wl.get("compact"):
+            from coda_b200 import SyntheticCompactDataset
+            ds = SyntheticCompactDataset(H, N, C, K=wl["K"], seed=args.seed, device=dev, rank=rank, world=world)
+        else:
+            ds = SyntheticDataset(H, N, C, seed=args.seed, device=dev, dense=dense, rank=rank, world=world)
         torch.cuda.synchronize()
         return ds, ds.labels.to(dev), ds.labels_host.numpy(), time.time() - t
 
@@ -502,7 +515,7 @@ def main():
         pm = eager_profile(sel, labels_dev, prof_steps)
         extra[m] = {"value": args.extra_steps / (ms_m / 1e3), "unit": "steps/s", "ms_per_step": ms_m / args.extra_steps,
                     "init_s": t_i, "roofline": roofline(eng, pm, ms_m / args.extra_steps, m), "kernel_ms": kernel_table(pm)}
-    if args.dense_extra and not args.dense and world == 1:
+    if args.dense_extra and not args.dense and world == 1 and not wl.get("compact"):
         # the dense worst case (wrong class uniform over all C) beside the default slab
         sel.close()
         del sel, eng, ds
@@ -519,7 +532,7 @@ def main():
                                "roofline": roofline(eng, pd, ms_d / (args.extra_steps * 2), eng.mode),
                                "kernel_ms": kernel_table(pd)}
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:      # rank 0, N=1 only (the reference arm covers N>1)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not wl.get("compact"):   # rank 0, N=1 only (the reference arm covers N>1)
         cpu = cpu_baseline(wl, args.cpu_seconds, args.seed, args.dense)
 
     if rank == 0:

@@ -646,8 +646,10 @@ __device__ __forceinline__ void rows_accumulate_reg(float* __restrict__ U, long 
 }
 
 #define R1_TN 256
-template <int KC>
-__global__ void __launch_bounds__(256) k_pi_rank1(const float* __restrict__ preds, const float* __restrict__ E,
+// GU: gathers in flight per lane, NR: U rows in flight per warp (more of both = more bytes in flight per SM at
+// the price of registers / resident warps)
+template <int KC, int GU = 16, int NR = 4>
+__global__ void __launch_bounds__(256, (GU > 16 ? 3 : 1)) k_pi_rank1(const float* __restrict__ preds, const float* __restrict__ E,
                                                   long long N, int C, const long long* __restrict__ sel,
                                                   const int32_t* __restrict__ hdr, const R1Term* __restrict__ gterms,
                                                   float lr, float fxs,
@@ -676,23 +678,23 @@ __global__ void __launch_bounds__(256) k_pi_rank1(const float* __restrict__ pred
     if (n < N) {
       if (tp >= 0) d = __ldg(E + (size_t)n * C + tp);
       int k = 0;
-      for (; k + 16 <= nt; k += 16) {
-        float v[16];
+      for (; k + GU <= nt; k += GU) {
+        float v[GU];
 #pragma unroll
-        for (int q = 0; q < 16; ++q) v[q] = __ldg(preds + c_terms[k + q].off + n * c_terms[k + q].str);
+        for (int q = 0; q < GU; ++q) v[q] = __ldg(preds + c_terms[k + q].off + n * c_terms[k + q].str);
 #pragma unroll
-        for (int q = 0; q < 16; ++q) d = fmaf(c_terms[k + q].sg, v[q], d);
+        for (int q = 0; q < GU; ++q) d = fmaf(c_terms[k + q].sg, v[q], d);
       }
       for (; k < nt; ++k) d = fmaf(c_terms[k].sg, __ldg(preds + c_terms[k].off + n * c_terms[k].str), d);
     }
     const float dl = lr * d;
     const int rows = (int)min(32LL, N - n0);
     if (KC > 0) {
-      for (int r = 0; r < rows; r += 4) {
-        float dv[4];
+      for (int r = 0; r < rows; r += NR) {
+        float dv[NR];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) dv[i] = __shfl_sync(CODA_FULL, dl, (r + i) & 31);
-        rows_accumulate_reg<(KC > 0 ? KC : 1), 4>(U, n0 + r, rows - r, 1, C, lane, fxs, t, dv, racc, bad);
+        for (int i = 0; i < NR; ++i) dv[i] = __shfl_sync(CODA_FULL, dl, (r + i) & 31);
+        rows_accumulate_reg<(KC > 0 ? KC : 1), NR>(U, n0 + r, rows - r, 1, C, lane, fxs, t, dv, racc, bad);
       }
     } else {
       for (int r = 0; r < rows; ++r) {
@@ -1017,6 +1019,7 @@ extern "C" int coda_b200_pi_rank1(const float* preds, const float* ens, int H, i
   const char* r1env = getenv("CODA_B200_R1");
   const bool want_tma = r1env && r1env[0] == 't';
   const bool want_v1 = !(r1env && r1env[0] == 'v' && r1env[1] == '4');
+  const bool want_deep = r1env && r1env[0] == 'v' && r1env[1] == '1' && r1env[2] == 'd';   // "v1d": 32 gathers / 8 rows in flight
   const bool no_tma = !want_tma;
   const int TR = C <= 128 ? r1x_tile_rows(C) : 0;
   if (!no_tma && TR >= 32 && (reinterpret_cast<uintptr_t>(U) & 15) == 0) {
@@ -1073,6 +1076,14 @@ extern "C" int coda_b200_pi_rank1(const float* preds, const float* ens, int H, i
                                             tlist, (float)lr, exp2f((float)fx_shift), U,                       \
                                             reinterpret_cast<unsigned long long*>(pisum_fx), flags);           \
   } while (0)
+  if (want_deep && C > 64 && C <= 128) {
+    CODA_CUDA_OK(cudaFuncSetAttribute(k_pi_rank1<4, 32, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_pi_rank1<4, 32, 8><<<grid, 256, smem, st>>>(preds, ens, N, C, reinterpret_cast<const long long*>(sel), hdr, tlist,
+                                                  (float)lr, exp2f((float)fx_shift), U,
+                                                  reinterpret_cast<unsigned long long*>(pisum_fx), flags);
+    CODA_LAUNCH_OK("k_pi_rank1<deep>");
+    return CODA_B200_OK;
+  }
   if (C <= 32) LAUNCH_R1(1);
   else if (C <= 64) LAUNCH_R1(2);
   else if (C <= 128) LAUNCH_R1(4);

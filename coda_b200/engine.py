@@ -633,9 +633,12 @@ class Engine:
         self._post_label()
         self._report()
 
-    def label(self, idx_global: int, true_class: int, eager_report: bool = True):
-        """coda.py:316-319 for a host-chosen (idx, class): stage the record, posterior update, marginal refresh and --
-        so that the next get_next_item_to_label only has to wait -- the next scoring pass + report.  Enqueue only."""
+    # add_label in phases (a front end driving several shards calls each phase on every shard before the next, so
+    # that nothing blocks the host -- a graph capture synchronises the device -- while a peer's kernels are missing):
+    #   label_stage    stage the host-chosen (idx, class) record: pinned ring slot -> device, no exchange inside
+    #   api_capture    (once, after two eager steps) capture label + refresh + scoring pass + report as one graph
+    #   label_run      replay the graph, or enqueue the same kernels one by one
+    def label_stage(self, idx_global: int, true_class: int):
         with self._on():
             k = self.sel_pos
             self.sel_pos = (k + 1) % len(self.sel_events)
@@ -648,25 +651,40 @@ class Engine:
             ev = torch.cuda.Event()
             ev.record(self._cur())
             self.sel_events[k] = ev
+
+    def api_graph_wanted(self) -> bool:
+        return (self.use_graph and self.graphs.get("api") is None and self.graphs.get("api_warm", 0) >= 2
+                and (self.cache_valid or self.mode != "incremental"))
+
+    def api_capture(self):
+        with self._on():
+            self.graphs["api"], self.launches_per_api_step = self._capture(self._api_body)
+
+    def label_run(self, eager_report: bool = True):
+        with self._on():
             if not eager_report:
                 self._call("coda_b200_step_label", self.st, self._x(), self._s())
                 self._post_label()
                 return
-            if self.use_graph and (self.cache_valid or self.mode != "incremental"):
-                g = self.graphs.get("api")
-                if g is None and self.graphs.get("api_warm", 0) >= 2:
-                    g, self.launches_per_api_step = self._capture(self._api_body)
-                    self.graphs["api"] = g
-                if g is not None:
-                    if self.pending:
-                        self._cur().wait_event(self.ev_join)
-                        self.pending = False
-                    g.replay()
-                    self.counters["launches"] += self.launches_per_api_step
-                    self.scored, self.reported = True, True
-                    return
-                self.graphs["api_warm"] = self.graphs.get("api_warm", 0) + 1
+            g = self.graphs.get("api") if self.use_graph else None
+            if g is not None:
+                if self.pending:
+                    self._cur().wait_event(self.ev_join)
+                    self.pending = False
+                g.replay()
+                self.counters["launches"] += self.launches_per_api_step
+                self.scored, self.reported = True, True
+                return
+            self.graphs["api_warm"] = self.graphs.get("api_warm", 0) + 1
             self._api_body()
+
+    def label(self, idx_global: int, true_class: int, eager_report: bool = True):
+        """coda.py:316-319 for a host-chosen (idx, class): stage the record, posterior update, marginal refresh and --
+        so that the next get_next_item_to_label only has to wait -- the next scoring pass + report.  Enqueue only."""
+        self.label_stage(idx_global, true_class)
+        if eager_report and self.api_graph_wanted():
+            self.api_capture()
+        self.label_run(eager_report)
 
     def fetch(self):
         """Wait for the report block and decode it.  Returns a dict of host values."""

@@ -294,8 +294,13 @@ class CODA(ModelSelector):
         if idx not in self.unlabeled_idxs:
             raise ValueError("list.remove(x): x not in list")
         eager = self.q == "eig" and not self.prefilter_n    # the next call will want the scores: enqueue them now
+        for e in self.engines:                              # phases in lock-step over the shards (see Engine.label_stage)
+            e.label_stage(idx, true_class)
+        if eager and all(e.api_graph_wanted() for e in self.engines):
+            for e in self.engines:
+                e.api_capture()
         for e in self.engines:
-            e.label(idx, true_class, eager_report=eager)
+            e.label_run(eager)
         self.labeled_idxs.append(idx)
         self.labels.append(true_class)
         self.q_vals.append(selection_prob)

@@ -49,8 +49,14 @@ class FakeEngine:
             names = [v for k, v in nat.FLAG_NAMES.items() if flags & k]
             raise RuntimeError(f"[NUMERIC ERROR] {', '.join(names)} has bad values (NaN/Inf)")
 
-    def label(self, idx, cls, eager_report=True):
+    def label_stage(self, idx, cls):
         self.posted.append((idx, cls))
+
+    def api_graph_wanted(self):
+        return False
+
+    def label_run(self, eager_report=True):
+        pass
 
     def mark_labeled(self, idx):
         self.marked.append(idx)

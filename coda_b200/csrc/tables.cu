@@ -96,18 +96,22 @@ __global__ void __launch_bounds__(TP_) k_beta_nodes(const float* __restrict__ D,
   if (bad) atomicOr(flags, bad);
 }
 
-// grid = (ncls, nsplit); block = 256 threads, one per node.  CTA (ci, sl) writes dL, G0T, G1T and the raw
-// "before" integrals for the models h = sl, sl + nsplit, ... of class ci.
+// grid = (ncls, nsplit); block = (256 nodes, NP parts).  Every CTA forms S0 / SB for its class: part p sums the
+// models h = p, p + NP, ... and the partial sums are combined in a fixed order, so every CTA (and every replica on
+// every GPU) computes the same bits.  Then part p of CTA (ci, sl) writes dL, G0T, G1T and the raw "before"
+// integrals for the models h = sl + nsplit * (p + NP * i).
 #define HSPLIT 8
-__global__ void __launch_bounds__(TP_) k_beta_combine(const double* __restrict__ pdf_s, const double* __restrict__ L_s,
-                                                      const float* __restrict__ grid_x, int H, int Hp, int cls_lo,
-                                                      const long long* __restrict__ sel, float* __restrict__ dL,
-                                                      float* __restrict__ G0T, float* __restrict__ G1T,
-                                                      __nv_bfloat16* __restrict__ dLb, __nv_bfloat16* __restrict__ Gb,
-                                                      double* __restrict__ pb_raw, uint32_t* __restrict__ flags) {
+template <int NP>
+__global__ void __launch_bounds__(TP_ * NP) k_beta_combine(const double* __restrict__ pdf_s, const double* __restrict__ L_s,
+                                                          const float* __restrict__ grid_x, int H, int Hp, int cls_lo,
+                                                          const long long* __restrict__ sel, float* __restrict__ dL,
+                                                          float* __restrict__ G0T, float* __restrict__ G1T,
+                                                          __nv_bfloat16* __restrict__ dLb, __nv_bfloat16* __restrict__ Gb,
+                                                          double* __restrict__ pb_raw, uint32_t* __restrict__ flags) {
   if (sel) cls_lo = (int)sel[1];
-  __shared__ double part[8];
-  const int ci = blockIdx.x, c = cls_lo + ci, x = threadIdx.x, ncls = gridDim.x;
+  __shared__ double part[NP][8];
+  __shared__ double s0p[NP][TP_], sbp[NP][TP_];
+  const int ci = blockIdx.x, c = cls_lo + ci, x = threadIdx.x, p = threadIdx.y, ncls = gridDim.x;
   const int lane = x & 31, warp = x >> 5;
   const size_t plane = (size_t)ncls * H * TP_;
   const double* Lb = L_s + 0 * plane + (size_t)ci * H * TP_;
@@ -121,55 +125,71 @@ __global__ void __launch_bounds__(TP_) k_beta_combine(const double* __restrict__
   const float dl_ = x > 0 ? xf - grid_x[x - 1] : 0.f;
   const float dr_ = x < TP_ - 1 ? grid_x[x + 1] - xf : 0.f;
   const double wq = 0.5 * ((double)dl_ + (double)dr_);
+  {
+    double a0 = 0.0, ab = 0.0;
+    for (int h = p; h < H; h += NP) {
+      a0 += Lm[(size_t)h * TP_ + x];
+      ab += Lb[(size_t)h * TP_ + x];
+    }
+    s0p[p][x] = a0;
+    sbp[p][x] = ab;
+  }
+  __syncthreads();
   double S0 = 0.0, SB = 0.0;
-  for (int h = 0; h < H; ++h) {   // every CTA of the class forms the same sums in the same order
-    S0 += Lm[(size_t)h * TP_ + x];
-    SB += Lb[(size_t)h * TP_ + x];
+#pragma unroll
+  for (int q = 0; q < NP; ++q) {      // fixed order
+    S0 += s0p[q][x];
+    SB += sbp[q][x];
   }
   uint32_t bad = 0;
-  for (int h = blockIdx.y; h < H; h += gridDim.y) {
-    const size_t o = (size_t)h * TP_ + x;
-    const double lm = Lm[o], lh = Lh[o], lb = Lb[o];
-    const double g0 = wq * pm[o] * exp(fmin(fmax(S0 - lm, -80.0), 80.0));
-    const double g1 = wq * ph[o] * exp(fmin(fmax(S0 - lh, -80.0), 80.0));
-    double ib = wq * pb[o] * exp(fmin(fmax(SB - lb, -80.0), 80.0));
-    const float g0f = (float)g0, g1f = (float)g1;
-    if (!isfinite(g0f) || !isfinite(g1f) || !isfinite(ib)) bad |= CODA_B200_FLAG_NONFINITE_TABLE;
-    const float dlf = (float)(lh - lm);
-    dL[((size_t)c * H + h) * TP_ + x] = dlf;
-    G0T[((size_t)c * TP_ + x) * Hp + h] = g0f;
-    G1T[((size_t)c * TP_ + x) * Hp + h] = g1f;
-    if (dLb) {
-      // tensor-core operand tables (pairs_tc.cu): bf16 limbs in the UMMA no-swizzle K-major core-matrix order
-      // [k_core][r_core][8 rows][8 elements].  dLb tile: rows = nodes, K = 32 models; Gb tile: rows = models, K = 16 nodes.
-      const __nv_bfloat16 d0 = __float2bfloat16_rn(dlf);
-      const float r1 = dlf - __bfloat162float(d0);
-      const __nv_bfloat16 d1 = __float2bfloat16_rn(r1);
-      const __nv_bfloat16 d2 = __float2bfloat16_rn(r1 - __bfloat162float(d1));
-      const size_t nka = (size_t)Hp / 32;
-      const size_t ta = ((size_t)c * nka + (h >> 5)) * 3 * (TP_ * 32);
-      const size_t ea = (size_t)((((h & 31) >> 3) * (TP_ / 8) + (x >> 3)) * 64 + (x & 7) * 8 + (h & 7));
-      dLb[ta + 0 * (TP_ * 32) + ea] = d0;
-      dLb[ta + 1 * (TP_ * 32) + ea] = d1;
-      dLb[ta + 2 * (TP_ * 32) + ea] = d2;
-      const __nv_bfloat16 a0 = __float2bfloat16_rn(g0f), b0 = __float2bfloat16_rn(g1f);
-      const __nv_bfloat16 a1 = __float2bfloat16_rn(g0f - __bfloat162float(a0));
-      const __nv_bfloat16 b1 = __float2bfloat16_rn(g1f - __bfloat162float(b0));
-      const size_t tsz = (size_t)Hp * 16;
-      const size_t tb = ((size_t)c * (TP_ / 16) + (x >> 4)) * 4 * tsz;
-      const size_t eb = (size_t)((((x & 15) >> 3) * (Hp / 8) + (h >> 3)) * 64 + (h & 7) * 8 + (x & 7));
-      Gb[tb + 0 * tsz + eb] = a0;
-      Gb[tb + 1 * tsz + eb] = a1;
-      Gb[tb + 2 * tsz + eb] = b0;
-      Gb[tb + 3 * tsz + eb] = b1;
+  const int niter = (H + gridDim.y * NP - 1) / (gridDim.y * NP);
+  for (int it = 0; it < niter; ++it) {
+    const int h = blockIdx.y + gridDim.y * (p + NP * it);
+    double ib = 0.0;
+    if (h < H) {
+      const size_t o = (size_t)h * TP_ + x;
+      const double lm = Lm[o], lh = Lh[o], lb = Lb[o];
+      const double g0 = wq * pm[o] * exp(fmin(fmax(S0 - lm, -80.0), 80.0));
+      const double g1 = wq * ph[o] * exp(fmin(fmax(S0 - lh, -80.0), 80.0));
+      ib = wq * pb[o] * exp(fmin(fmax(SB - lb, -80.0), 80.0));
+      const float g0f = (float)g0, g1f = (float)g1;
+      if (!isfinite(g0f) || !isfinite(g1f) || !isfinite(ib)) bad |= CODA_B200_FLAG_NONFINITE_TABLE;
+      const float dlf = (float)(lh - lm);
+      dL[((size_t)c * H + h) * TP_ + x] = dlf;
+      G0T[((size_t)c * TP_ + x) * Hp + h] = g0f;
+      G1T[((size_t)c * TP_ + x) * Hp + h] = g1f;
+      if (dLb) {
+        // tensor-core operand tables (pairs_tc.cu): bf16 limbs in the UMMA no-swizzle K-major core-matrix order
+        // [k_core][r_core][8 rows][8 elements].  dLb tile: rows = nodes, K = 32 models; Gb tile: rows = models, K = 16 nodes.
+        const __nv_bfloat16 d0 = __float2bfloat16_rn(dlf);
+        const float r1 = dlf - __bfloat162float(d0);
+        const __nv_bfloat16 d1 = __float2bfloat16_rn(r1);
+        const __nv_bfloat16 d2 = __float2bfloat16_rn(r1 - __bfloat162float(d1));
+        const size_t nka = (size_t)Hp / 32;
+        const size_t ta = ((size_t)c * nka + (h >> 5)) * 3 * (TP_ * 32);
+        const size_t ea = (size_t)((((h & 31) >> 3) * (TP_ / 8) + (x >> 3)) * 64 + (x & 7) * 8 + (h & 7));
+        dLb[ta + 0 * (TP_ * 32) + ea] = d0;
+        dLb[ta + 1 * (TP_ * 32) + ea] = d1;
+        dLb[ta + 2 * (TP_ * 32) + ea] = d2;
+        const __nv_bfloat16 a0 = __float2bfloat16_rn(g0f), b0 = __float2bfloat16_rn(g1f);
+        const __nv_bfloat16 a1 = __float2bfloat16_rn(g0f - __bfloat162float(a0));
+        const __nv_bfloat16 b1 = __float2bfloat16_rn(g1f - __bfloat162float(b0));
+        const size_t tsz = (size_t)Hp * 16;
+        const size_t tb = ((size_t)c * (TP_ / 16) + (x >> 4)) * 4 * tsz;
+        const size_t eb = (size_t)((((x & 15) >> 3) * (Hp / 8) + (h >> 3)) * 64 + (h & 7) * 8 + (x & 7));
+        Gb[tb + 0 * tsz + eb] = a0;
+        Gb[tb + 1 * tsz + eb] = a1;
+        Gb[tb + 2 * tsz + eb] = b0;
+        Gb[tb + 3 * tsz + eb] = b1;
+      }
     }
     ib = warp_sum(ib);
     __syncthreads();
-    if (lane == 0) part[warp] = ib;
+    if (lane == 0) part[p][warp] = ib;
     __syncthreads();
-    if (x == 0) {
+    if (x == 0 && h < H) {
       double sum = 0.0;
-      for (int w8 = 0; w8 < 8; ++w8) sum += part[w8];   // fixed order
+      for (int w8 = 0; w8 < 8; ++w8) sum += part[p][w8];   // fixed order
       pb_raw[(size_t)ci * Hp + h] = sum;
     }
   }
@@ -219,10 +239,15 @@ extern "C" int coda_b200_beta_tables(const float* D, const float* grid_x, int H,
   dim3 g1((unsigned)H, (unsigned)ncls);
   k_beta_nodes<<<g1, TP_, 0, as_stream(stream)>>>(D, grid_x, H, C, cls_lo, (float)hyp_w, seld, pdf_s, L_s, flags);
   CODA_LAUNCH_OK("k_beta_nodes");
-  // few classes (the per-step single-class refresh): spread the models over more CTAs
-  dim3 g2((unsigned)ncls, (unsigned)(ncls >= 16 ? HSPLIT : (H < 64 ? H : 64)));
-  k_beta_combine<<<g2, TP_, 0, as_stream(stream)>>>(pdf_s, L_s, grid_x, H, Hp, cls_lo, seld, dL, G0T, G1T,
-                                                    reinterpret_cast<__nv_bfloat16*>(dLb), reinterpret_cast<__nv_bfloat16*>(Gb), pb_raw, flags);
+  {
+    // the S0 / SB sums are split over four parts per node in BOTH launch shapes: a class table must carry the same bits
+    // whether it was built alone (per-step refresh, on the critical path of a sharded step) or in a batch (construction,
+    // checkpoint resume).  Few classes: spread the models over more CTAs.
+    const int split = ncls >= 16 ? (H / 4 < HSPLIT ? (H / 4 > 0 ? H / 4 : 1) : HSPLIT) : (H <= 4 ? 1 : (H / 4 < 64 ? H / 4 : 64));
+    dim3 g2((unsigned)ncls, (unsigned)split), b2(TP_, 4);
+    k_beta_combine<4><<<g2, b2, 0, as_stream(stream)>>>(pdf_s, L_s, grid_x, H, Hp, cls_lo, seld, dL, G0T, G1T,
+                                                        reinterpret_cast<__nv_bfloat16*>(dLb), reinterpret_cast<__nv_bfloat16*>(Gb), pb_raw, flags);
+  }
   CODA_LAUNCH_OK("k_beta_combine");
   k_pb_normalize<<<ncls, TP_, 0, as_stream(stream)>>>(pb_raw, H, Hp, cls_lo, seld, PB, flags);
   CODA_LAUNCH_OK("k_pb_normalize");

@@ -18,18 +18,53 @@
 
 #define CK_MAX 8
 
-__device__ __forceinline__ float compact_rest(const float* p, int K, float inv_cmk) {
+template <int K>
+__device__ __forceinline__ float compact_rest(const float (&p)[K], float inv_cmk) {
   float s = p[0];
+#pragma unroll
   for (int j = 1; j < K; ++j) s += p[j];
   return (1.0f - s) * inv_cmk;
 }
+
+// one (model, item) entry: K ids + K scores; K = 4 with aligned arrays is one 8-byte and one 16-byte load
+template <int K>
+__device__ __forceinline__ void compact_load(const uint16_t* __restrict__ ids, const float* __restrict__ probs, size_t e,
+                                             float (&p)[K], int (&id)[K]) {
+  if (K == 4 && ((reinterpret_cast<uintptr_t>(ids + e) & 7) == 0) && ((reinterpret_cast<uintptr_t>(probs + e) & 15) == 0)) {
+    const uint2 w = __ldg(reinterpret_cast<const uint2*>(ids + e));
+    const float4 f = __ldg(reinterpret_cast<const float4*>(probs + e));
+    id[0] = w.x & 0xFFFF; id[1] = w.x >> 16; id[2 % K] = w.y & 0xFFFF; id[3 % K] = w.y >> 16;
+    p[0] = f.x; p[1 % K] = f.y; p[2 % K] = f.z; p[3 % K] = f.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      p[j] = __ldg(probs + e + j);
+      id[j] = ids[e + j];
+    }
+  }
+}
+
+#define CK_DISPATCH(K, ...)                                    \
+  do {                                                         \
+    switch (K) {                                               \
+      case 1: { constexpr int KK = 1; __VA_ARGS__; } break;           \
+      case 2: { constexpr int KK = 2; __VA_ARGS__; } break;           \
+      case 3: { constexpr int KK = 3; __VA_ARGS__; } break;           \
+      case 4: { constexpr int KK = 4; __VA_ARGS__; } break;           \
+      case 8: { constexpr int KK = 8; __VA_ARGS__; } break;           \
+      default:                                                 \
+        coda_set_error("compact slab: K=%d not instantiated (1, 2, 3, 4, 8)", K); \
+        return CODA_B200_EINVAL;                               \
+    }                                                          \
+  } while (0)
 
 // ---------------------------------------------------------------------------------------
 // scan_compact: one thread per item (lanes <-> consecutive items: coalesced entry loads), models in order;
 // the item's ensemble row lives in shared memory (row stride padded to an odd word count).
 // ---------------------------------------------------------------------------------------
+template <int K>
 __global__ void __launch_bounds__(256) k_scan_compact(const uint16_t* __restrict__ ids, const float* __restrict__ probs,
-                                                      int H, long long N, int C, int K, long long model_stride_e,
+                                                      int H, long long N, int C, long long model_stride_e,
                                                       uint16_t* __restrict__ hard, int32_t* __restrict__ pseudo,
                                                       uint8_t* __restrict__ disagree, float* __restrict__ ens_out,
                                                       uint32_t* __restrict__ flags) {
@@ -47,17 +82,18 @@ __global__ void __launch_bounds__(256) k_scan_compact(const uint16_t* __restrict
   if (valid) {
     for (int h = 0; h < H; ++h) {
       const size_t e = (size_t)h * model_stride_e + (size_t)n * K;
-      float p[CK_MAX];
-      int id[CK_MAX];
+      float p[K];
+      int id[K];
+      compact_load<K>(ids, probs, e, p, id);
+#pragma unroll
       for (int j = 0; j < K; ++j) {
-        p[j] = __ldg(probs + e + j);
-        id[j] = ids[e + j];
         if (!isfinite(p[j])) bad |= CODA_B200_FLAG_NONFINITE_INPUT;
         if (p[j] < 0.f || p[j] > 1.0001f || id[j] >= C) bad |= CODA_B200_FLAG_RANGE_INPUT;
       }
-      const float r = compact_rest(p, K, inv_cmk);
+      const float r = compact_rest<K>(p, inv_cmk);
       if (r < -1e-6f) bad |= CODA_B200_FLAG_RANGE_INPUT;
       rsum += r;
+#pragma unroll
       for (int j = 0; j < K; ++j)
         if (id[j] < C) row[id[j]] += p[j] - r;
       hard[(size_t)n * H + h] = (uint16_t)id[0];               // ids are sorted by score: the first is the argmax
@@ -89,10 +125,12 @@ extern "C" int coda_b200_scan_compact(const uint16_t* ids, const float* probs, i
   while (threads > 32 && (size_t)threads * cpad * 4 > 200 * 1024) threads >>= 1;
   const size_t smem = (size_t)threads * cpad * 4;
   CODA_CHECK_ARG(smem <= 200 * 1024, "scan_compact: C=%d too large for the compact path", C);
-  CODA_CUDA_OK(cudaFuncSetAttribute(k_scan_compact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long grid = (N + threads - 1) / threads;
-  k_scan_compact<<<(unsigned)grid, threads, smem, as_stream(stream)>>>(ids, probs, H, N, C, K, (long long)model_stride, hard,
-                                                                       pseudo, disagree, ens_out, flags);
+  CK_DISPATCH(K, {
+    CODA_CUDA_OK(cudaFuncSetAttribute(k_scan_compact<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_scan_compact<KK><<<(unsigned)grid, threads, smem, as_stream(stream)>>>(ids, probs, H, N, C, (long long)model_stride,
+                                                                             hard, pseudo, disagree, ens_out, flags);
+  });
   CODA_LAUNCH_OK("k_scan_compact");
   return CODA_B200_OK;
 }
@@ -102,8 +140,9 @@ extern "C" int coda_b200_scan_compact(const uint16_t* ids, const float* probs, i
 // conf[h][y][j] of the densified slab == conf_fx[h][y][j] + conf_rest[h][y] exactly (integer sums).
 // grid = (item chunks, H); lanes <-> consecutive items.
 // ---------------------------------------------------------------------------------------
+template <int K>
 __global__ void __launch_bounds__(256) k_confusion_compact(const uint16_t* __restrict__ ids, const float* __restrict__ probs,
-                                                           const int32_t* __restrict__ pseudo, long long N, int C, int K,
+                                                           const int32_t* __restrict__ pseudo, long long N, int C,
                                                            long long model_stride_e, float fxs,
                                                            unsigned long long* __restrict__ conf_fx,
                                                            unsigned long long* __restrict__ conf_rest) {
@@ -112,17 +151,15 @@ __global__ void __launch_bounds__(256) k_confusion_compact(const uint16_t* __res
   if (n >= N) return;
   const float inv_cmk = 1.0f / (float)(C - K);
   const size_t e = (size_t)h * model_stride_e + (size_t)n * K;
-  float p[CK_MAX];
-  int id[CK_MAX];
-  for (int j = 0; j < K; ++j) {
-    p[j] = __ldg(probs + e + j);
-    id[j] = ids[e + j];
-  }
-  const float r = compact_rest(p, K, inv_cmk);
+  float p[K];
+  int id[K];
+  compact_load<K>(ids, probs, e, p, id);
+  const float r = compact_rest<K>(p, inv_cmk);
   const long long fr = to_fx(r, fxs);
   const int y = pseudo[n];
   unsigned long long* tab = conf_fx + ((size_t)h * C + y) * C;
   if (fr) atomicAdd(conf_rest + (size_t)h * C + y, (unsigned long long)fr);
+#pragma unroll
   for (int j = 0; j < K; ++j) {
     const long long v = to_fx(p[j], fxs) - fr;
     if (v && id[j] < C) atomicAdd(tab + id[j], (unsigned long long)v);
@@ -136,10 +173,9 @@ extern "C" int coda_b200_confusion_compact(const uint16_t* ids, const float* pro
   CODA_CHECK_ARG(K >= 1 && K <= CK_MAX && K < C, "confusion_compact: bad K=%d", K);
   CODA_CHECK_ARG(fx_shift >= 8 && fx_shift <= 46, "confusion_compact: bad fx_shift %d", fx_shift);
   dim3 grid((unsigned)((N + 255) / 256), (unsigned)H);
-  k_confusion_compact<<<grid, 256, 0, as_stream(stream)>>>(ids, probs, pseudo, N, C, K, (long long)model_stride,
-                                                           exp2f((float)fx_shift),
-                                                           reinterpret_cast<unsigned long long*>(conf_fx),
-                                                           reinterpret_cast<unsigned long long*>(conf_rest));
+  CK_DISPATCH(K, (k_confusion_compact<KK><<<grid, 256, 0, as_stream(stream)>>>(
+                         ids, probs, pseudo, N, C, (long long)model_stride, exp2f((float)fx_shift),
+                         reinterpret_cast<unsigned long long*>(conf_fx), reinterpret_cast<unsigned long long*>(conf_rest))));
   CODA_LAUNCH_OK("k_confusion_compact");
   return CODA_B200_OK;
 }
@@ -177,9 +213,9 @@ __global__ void k_rowsum_D(const float* __restrict__ D, long long rows, int C, f
 }
 
 // one warp per item, the item's U row in registers (C <= 32 * KCU); models in order.
-template <int KCU>
+template <int KCU, int K>
 __global__ void __launch_bounds__(256) k_pi_full_compact(const uint16_t* __restrict__ ids, const float* __restrict__ probs,
-                                                         int H, long long N, int C, int K, long long model_stride_e,
+                                                         int H, long long N, int C, long long model_stride_e,
                                                          const float* __restrict__ DT, const float* __restrict__ RS,
                                                          float* __restrict__ U) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -190,19 +226,17 @@ __global__ void __launch_bounds__(256) k_pi_full_compact(const uint16_t* __restr
     for (int k = 0; k < KCU; ++k) u[k] = 0.f;
     for (int h = 0; h < H; ++h) {
       const size_t e = (size_t)h * model_stride_e + (size_t)n * K;
-      float p[CK_MAX];
-      int id[CK_MAX];
-      for (int j = 0; j < K; ++j) {                 // broadcast loads (every lane the same address)
-        p[j] = __ldg(probs + e + j);
-        id[j] = ids[e + j];
-      }
-      const float r = compact_rest(p, K, inv_cmk);
+      float p[K];
+      int id[K];
+      compact_load<K>(ids, probs, e, p, id);          // broadcast loads (every lane the same address)
+      const float r = compact_rest<K>(p, inv_cmk);
       const float* rs = RS + (size_t)h * C;
 #pragma unroll
       for (int k = 0; k < KCU; ++k) {
         const int c = lane + 32 * k;
         if (c < C) u[k] = fmaf(r, __ldg(rs + c), u[k]);
       }
+#pragma unroll
       for (int j = 0; j < K; ++j) {
         if (id[j] >= C) continue;
         const float w = p[j] - r;
@@ -237,7 +271,7 @@ extern "C" int coda_b200_pi_full_compact(const uint16_t* ids, const float* probs
   int grid = (int)min((long long)(N + 7) / 8, (long long)coda_sm_count() * 8);
   if (grid < 1) grid = 1;
 #define LAUNCH_PFC(KCU) \
-  k_pi_full_compact<KCU><<<grid, 256, 0, st>>>(ids, probs, H, N, C, K, (long long)model_stride, DT_scratch, RS_scratch, U)
+  CK_DISPATCH(K, (k_pi_full_compact<KCU, KK><<<grid, 256, 0, st>>>(ids, probs, H, N, C, (long long)model_stride, DT_scratch, RS_scratch, U)))
   if (C <= 32) LAUNCH_PFC(1);
   else if (C <= 64) LAUNCH_PFC(2);
   else if (C <= 128) LAUNCH_PFC(4);
@@ -254,8 +288,9 @@ extern "C" int coda_b200_pi_full_compact(const uint16_t* ids, const float* probs
 // kernels with coda_step_t.compact_k > 0): term = {off = model h, sg = +-1, str = class j}: value = K-way match.
 // lanes <-> consecutive items (coalesced 8/16-byte entry loads), then the warp walks its 32 rows of U.
 // ---------------------------------------------------------------------------------------
+template <int K>
 __global__ void __launch_bounds__(256) k_pi_rank1_compact(const uint16_t* __restrict__ ids, const float* __restrict__ probs,
-                                                          const float* __restrict__ E, long long N, int C, int K,
+                                                          const float* __restrict__ E, long long N, int C,
                                                           long long model_stride_e, const long long* __restrict__ sel,
                                                           const int32_t* __restrict__ hdr, const R1Term* __restrict__ gterms,
                                                           float lr, float fxs, float* __restrict__ U,
@@ -279,20 +314,19 @@ __global__ void __launch_bounds__(256) k_pi_rank1_compact(const uint16_t* __rest
     if (n < N) {
       if (tp >= 0) d = __ldg(E + (size_t)n * C + tp);
       long long cur = -1;
-      float p[CK_MAX], r = 0.f;
-      int id[CK_MAX];
+      float p[K], r = 0.f;
+      int id[K];
+#pragma unroll
+      for (int j = 0; j < K; ++j) { p[j] = 0.f; id[j] = -1; }
       for (int k = 0; k < nt; ++k) {
         const R1Term tm = terms[k];
         if (tm.off != cur) {                         // the two terms of one model share its entry
           cur = tm.off;
-          const size_t e = (size_t)cur * model_stride_e + (size_t)n * K;
-          for (int j = 0; j < K; ++j) {
-            p[j] = __ldg(probs + e + j);
-            id[j] = ids[e + j];
-          }
-          r = compact_rest(p, K, inv_cmk);
+          compact_load<K>(ids, probs, (size_t)cur * model_stride_e + (size_t)n * K, p, id);
+          r = compact_rest<K>(p, inv_cmk);
         }
         float v = r;
+#pragma unroll
         for (int j = 0; j < K; ++j)
           if (id[j] == tm.str) v = p[j];
         d = fmaf(tm.sg, v, d);
@@ -335,13 +369,15 @@ extern "C" int coda_b200_pi_rank1_compact(const uint16_t* ids, const float* prob
   CODA_CHECK_ARG(K >= 1 && K <= CK_MAX && K < C && 2 * H <= R1_MAXT, "pi_rank1_compact: bad dims");
   const size_t smem = (size_t)8 * C * 8 + (size_t)2 * H * sizeof(R1Term);
   CODA_CHECK_ARG(smem <= 200 * 1024, "pi_rank1_compact: C=%d too large", C);
-  CODA_CUDA_OK(cudaFuncSetAttribute(k_pi_rank1_compact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = (int)min((long long)(N + 255) / 256, (long long)coda_sm_count() * 4);
   if (grid < 1) grid = 1;
-  k_pi_rank1_compact<<<grid, 256, smem, as_stream(stream)>>>(
-      ids, probs, ens, N, C, K, (long long)model_stride, reinterpret_cast<const long long*>(sel), terms,
-      reinterpret_cast<const R1Term*>(terms + 2), (float)lr, exp2f((float)fx_shift), U,
-      reinterpret_cast<unsigned long long*>(pisum_fx), flags);
+  CK_DISPATCH(K, {
+    CODA_CUDA_OK(cudaFuncSetAttribute(k_pi_rank1_compact<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_pi_rank1_compact<KK><<<grid, 256, smem, as_stream(stream)>>>(
+        ids, probs, ens, N, C, (long long)model_stride, reinterpret_cast<const long long*>(sel), terms,
+        reinterpret_cast<const R1Term*>(terms + 2), (float)lr, exp2f((float)fx_shift), U,
+        reinterpret_cast<unsigned long long*>(pisum_fx), flags);
+  });
   CODA_LAUNCH_OK("k_pi_rank1_compact");
   return CODA_B200_OK;
 }

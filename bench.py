@@ -292,7 +292,7 @@ def algorithmic_bytes(eng):
     lists = 6 * N * eng.ell_k if eng.ell_row is not None else 6 * ent + 8 * N
     return {
         # the cached row of every heavy (item, class) + its class id; writes one gain per row
-        "coda_b200_row_gains": 4 * heavy * Hp + 2 * heavy + 4 * heavy,
+        "coda_b200_row_gains": 4 * eng.npairs * Hp + 2 * heavy + 4 * eng.npairs,
         # U rows + entry lists + one gain per entry + candidate masks; writes eig
         "coda_b200_gain_eig": ((4 * heavy * Hp) if getattr(eng, "fused_score", False) else 0) + 4 * N * C + lists + 4 * ent
                               + 2 * N + 4 * N,

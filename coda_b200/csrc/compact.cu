@@ -288,7 +288,8 @@ extern "C" int coda_b200_pi_full_compact(const uint16_t* ids, const float* probs
 // kernels with coda_step_t.compact_k > 0): term = {off = model h, sg = +-1, str = class j}: value = K-way match.
 // lanes <-> consecutive items (coalesced 8/16-byte entry loads), then the warp walks its 32 rows of U.
 // ---------------------------------------------------------------------------------------
-template <int K>
+// KCU: C <= 32 * KCU keeps the int64 column sums (and one U row) in registers; KCU = 0: any C, shared-memory sums
+template <int K, int KCU>
 __global__ void __launch_bounds__(256) k_pi_rank1_compact(const uint16_t* __restrict__ ids, const float* __restrict__ probs,
                                                           const float* __restrict__ E, long long N, int C,
                                                           long long model_stride_e, const long long* __restrict__ sel,
@@ -308,6 +309,9 @@ __global__ void __launch_bounds__(256) k_pi_rank1_compact(const uint16_t* __rest
   __syncthreads();
   const float inv_cmk = 1.0f / (float)(C - K);
   uint32_t bad = 0;
+  long long racc[KCU > 0 ? KCU : 1];
+#pragma unroll
+  for (int k = 0; k < (KCU > 0 ? KCU : 1); ++k) racc[k] = 0;
   for (long long n0 = (long long)blockIdx.x * 256 + warp * 32; n0 < N; n0 += (long long)gridDim.x * 256) {
     const long long n = n0 + lane;
     float d = 0.f;
@@ -337,6 +341,27 @@ __global__ void __launch_bounds__(256) k_pi_rank1_compact(const uint16_t* __rest
     for (int r2 = 0; r2 < rows; ++r2) {
       const float dr = __shfl_sync(CODA_FULL, dl, r2);
       float* urow = U + (size_t)(n0 + r2) * C;
+      if (KCU > 0) {
+        constexpr int KR = KCU > 0 ? KCU : 1;
+        float u[KR];
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < KR; ++k) {
+          const int c = lane + 32 * k;
+          u[k] = c < C ? urow[c] : 0.f;
+          if (c == t) {
+            u[k] += dr;
+            urow[c] = u[k];
+          }
+          s += u[k];
+        }
+        s = warp_sum(s);
+        if (!isfinite(s)) bad |= CODA_B200_FLAG_NONFINITE_PI;
+        const float den = fmaxf(s, 1e-12f);                             // coda.py:230 clamp_(min=1e-12)
+#pragma unroll
+        for (int k = 0; k < KR; ++k) racc[k] += to_fx(u[k] / den, fxs);
+        continue;
+      }
       float s = 0.f;
       for (int c = lane; c < C; c += 32) {
         float u = urow[c];
@@ -350,6 +375,13 @@ __global__ void __launch_bounds__(256) k_pi_rank1_compact(const uint16_t* __rest
       if (!isfinite(s)) bad |= CODA_B200_FLAG_NONFINITE_PI;
       const float den = fmaxf(s, 1e-12f);                               // coda.py:230 clamp_(min=1e-12)
       for (int c = lane; c < C; c += 32) wacc[c] += to_fx(urow[c] / den, fxs);   // column t was rewritten by this lane
+    }
+  }
+  if (KCU > 0) {
+#pragma unroll
+    for (int k = 0; k < (KCU > 0 ? KCU : 1); ++k) {
+      const int c = lane + 32 * k;
+      if (c < C) wacc[c] = racc[k];
     }
   }
   __syncthreads();
@@ -371,13 +403,19 @@ extern "C" int coda_b200_pi_rank1_compact(const uint16_t* ids, const float* prob
   CODA_CHECK_ARG(smem <= 200 * 1024, "pi_rank1_compact: C=%d too large", C);
   int grid = (int)min((long long)(N + 255) / 256, (long long)coda_sm_count() * 4);
   if (grid < 1) grid = 1;
-  CK_DISPATCH(K, {
-    CODA_CUDA_OK(cudaFuncSetAttribute(k_pi_rank1_compact<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_pi_rank1_compact<KK><<<grid, 256, smem, as_stream(stream)>>>(
-        ids, probs, ens, N, C, (long long)model_stride, reinterpret_cast<const long long*>(sel), terms,
-        reinterpret_cast<const R1Term*>(terms + 2), (float)lr, exp2f((float)fx_shift), U,
-        reinterpret_cast<unsigned long long*>(pisum_fx), flags);
-  });
+#define LAUNCH_R1C(KCU)                                                                                                  \
+  CK_DISPATCH(K, {                                                                                                       \
+    CODA_CUDA_OK(cudaFuncSetAttribute(k_pi_rank1_compact<KK, KCU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    k_pi_rank1_compact<KK, KCU><<<grid, 256, smem, as_stream(stream)>>>(                                                  \
+        ids, probs, ens, N, C, (long long)model_stride, reinterpret_cast<const long long*>(sel), terms,                  \
+        reinterpret_cast<const R1Term*>(terms + 2), (float)lr, exp2f((float)fx_shift), U,                                \
+        reinterpret_cast<unsigned long long*>(pisum_fx), flags);                                                         \
+  })
+  if (C <= 128) LAUNCH_R1C(4);
+  else if (C <= 512) LAUNCH_R1C(16);
+  else if (C <= 1024) LAUNCH_R1C(32);
+  else LAUNCH_R1C(0);
+#undef LAUNCH_R1C
   CODA_LAUNCH_OK("k_pi_rank1_compact");
   return CODA_B200_OK;
 }

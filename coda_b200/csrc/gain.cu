@@ -12,6 +12,8 @@
 // Candidate filter (coda.py:215-219, 239) and the arg-max with runner-up (coda.py:306-309) ride along.
 #include "common.cuh"
 
+#include <stdlib.h>
+
 #define GE_THREADS 384
 #define GE_WARPS (GE_THREADS / 32)
 
@@ -280,7 +282,7 @@ __device__ __forceinline__ float4 ld_stream4(const float4* p) {
 
 template <int NQ>
 __global__ void __launch_bounds__(256) k_row_gains(const float* __restrict__ rows, const uint16_t* __restrict__ row_cls,
-                                                   long long nrows, int H, const float* __restrict__ PB,
+                                                   long long nrows, long long T, int H, const float* __restrict__ PB,
                                                    const float* __restrict__ m0, const float* __restrict__ pi_hat,
                                                    float* __restrict__ gain) {
   constexpr int Hp = 128 * NQ;
@@ -302,7 +304,9 @@ __global__ void __launch_bounds__(256) k_row_gains(const float* __restrict__ row
   for (long long ch = (long long)blockIdx.x * 8 + warp; ch < nchunks; ch += (long long)gridDim.x * 8) {
     const long long p0 = ch * CH;
     const long long p1 = min(nrows, p0 + CH);
-    const int mycls = (p0 + lane < p1) ? (int)row_cls[p0 + lane] : 0;     // classes of the whole chunk, one per lane
+    // classes of the whole chunk, one per lane: template rows (r < T) are class-major, heavy rows carry row_cls
+    int mycls = 0;
+    if (p0 + lane < p1) mycls = (p0 + lane < T) ? (int)((p0 + lane) / (1 + H)) : (int)row_cls[p0 + lane - T];
     for (long long i = p0; i < p1; i += 4) {
       float4 a[4][NQ];
 #pragma unroll
@@ -332,7 +336,7 @@ __global__ void __launch_bounds__(256) k_row_gains(const float* __restrict__ row
 
 // any Hp (multiple of 32): m0 / f(m0) in shared memory, one row at a time
 __global__ void __launch_bounds__(256) k_row_gains_any(const float* __restrict__ rows, const uint16_t* __restrict__ row_cls,
-                                                       long long nrows, int H, int Hp, const float* __restrict__ PB,
+                                                       long long nrows, long long T, int H, int Hp, const float* __restrict__ PB,
                                                        const float* __restrict__ m0, const float* __restrict__ pi_hat,
                                                        float* __restrict__ gain) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -346,7 +350,7 @@ __global__ void __launch_bounds__(256) k_row_gains_any(const float* __restrict__
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (long long r = (long long)blockIdx.x * 8 + warp; r < nrows; r += (long long)gridDim.x * 8) {
-    const int c = row_cls[r];
+    const int c = r < T ? (int)(r / (1 + H)) : (int)row_cls[r - T];
     const float pic = pi_hat[c];
     const float* row = rows + (size_t)r * Hp;
     const float* pb = PB + (size_t)c * Hp;
@@ -367,16 +371,16 @@ extern "C" int coda_b200_row_gains(const float* ph_cache, const uint16_t* row_cl
                                    const float* PB, const float* m0, const float* pi_hat, float* gain,
                                    coda_stream_t stream) {
   CODA_CHECK_ARG(ph_cache && PB && m0 && pi_hat && gain && (row_cls || n_heavy == 0), "row_gains: null pointer");
-  if (n_heavy <= 0) return CODA_B200_OK;
   const int Hp = (H + 31) / 32 * 32;
   const long long T = (long long)C * (1 + H);
-  const float* rows = ph_cache + (size_t)T * Hp;
-  float* g = gain + T;
+  const long long nrows = T + (n_heavy > 0 ? n_heavy : 0);      // template rows first, then the heavy rows: one stream
+  const float* rows = ph_cache;
+  float* g = gain;
   cudaStream_t st = as_stream(stream);
   if (Hp % 128 == 0 && Hp <= 512) {
-    int grid = (int)min((long long)(n_heavy + 255) / 256, (long long)coda_sm_count() * 6);
+    int grid = (int)min((long long)(nrows + 255) / 256, (long long)coda_sm_count() * 6);
     if (grid < 1) grid = 1;
-#define LAUNCH_RG(NQ) k_row_gains<NQ><<<grid, 256, 0, st>>>(rows, row_cls, n_heavy, H, PB, m0, pi_hat, g)
+#define LAUNCH_RG(NQ) k_row_gains<NQ><<<grid, 256, 0, st>>>(rows, row_cls, nrows, T, H, PB, m0, pi_hat, g)
     if (Hp == 128) LAUNCH_RG(1);
     else if (Hp == 256) LAUNCH_RG(2);
     else if (Hp == 384) LAUNCH_RG(3);
@@ -385,9 +389,9 @@ extern "C" int coda_b200_row_gains(const float* ph_cache, const uint16_t* row_cl
     CODA_LAUNCH_OK("k_row_gains");
     return CODA_B200_OK;
   }
-  int grid = (int)min((long long)(n_heavy + 7) / 8, (long long)coda_sm_count() * 8);
+  int grid = (int)min((long long)(nrows + 7) / 8, (long long)coda_sm_count() * 8);
   if (grid < 1) grid = 1;
-  k_row_gains_any<<<grid, 256, (size_t)2 * Hp * 4, st>>>(rows, row_cls, n_heavy, H, Hp, PB, m0, pi_hat, g);
+  k_row_gains_any<<<grid, 256, (size_t)2 * Hp * 4, st>>>(rows, row_cls, nrows, T, H, Hp, PB, m0, pi_hat, g);
   CODA_LAUNCH_OK("k_row_gains_any");
   return CODA_B200_OK;
 }
@@ -397,8 +401,8 @@ extern "C" int coda_b200_row_gains(const float* ph_cache, const uint16_t* row_cl
 // instruction, IT8 batches in flight; three dependent load levels (offsets -> entries + U row -> gains), each
 // issued for all items of the batch before the first use.
 // ---------------------------------------------------------------------------------------
-template <int KC8>
-__global__ void __launch_bounds__(256) k_eig_assemble_g8(GainEigArgs a, int nblocks_rec) {
+template <int KC8, int IT8>
+__global__ void __launch_bounds__(256, (IT8 == 1 ? 3 : 2)) k_eig_assemble_g8(GainEigArgs a, int nblocks_rec) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* g0 = reinterpret_cast<float*>(smem_raw);   // [C]
   __shared__ float s_v[2][8], s_v2[2][8];
@@ -410,7 +414,6 @@ __global__ void __launch_bounds__(256) k_eig_assemble_g8(GainEigArgs a, int nblo
   Best2 bA = best2_empty(), bB = best2_empty();
   long long cntA = 0;
   uint32_t bad = 0;
-  constexpr int IT8 = 2;
   const long long per_iter = (long long)gridDim.x * 8 * 4 * IT8;
   // the loop bound is warp-uniform (full-mask shuffles inside); a group past the end clamps its loads and skips its writes
   for (long long wb = ((long long)blockIdx.x * 8 + warp) * 4 * IT8; wb < a.N; wb += per_iter) {
@@ -531,7 +534,7 @@ static bool gain_eig_pb_in_smem(int C, int Hp) { return (size_t)C * Hp * 4 <= 10
 extern "C" int coda_b200_eig_blocks(int64_t N, int H, int C) {
   (void)H; (void)C;
   long long want = (N + GE_WARPS - 1) / GE_WARPS;
-  long long cap = (long long)coda_sm_count() * 2;
+  long long cap = (long long)coda_sm_count() * 4;
   return (int)(want < cap ? (want < 1 ? 1 : want) : cap);
 }
 
@@ -562,11 +565,18 @@ extern "C" int coda_b200_gain_eig(const float* U, int64_t N, int C, int H, const
   const int grid = coda_b200_eig_blocks(N, H, C);
   cudaStream_t st = as_stream(stream);
   if (!from_cache && C <= 128 && max_entries >= 0 && max_entries <= 32) {
-    // 8-lane groups: the grid may be larger than the record count the caller merges -- cap it there
-    int g8 = (int)min((long long)(N + 31) / 32, (long long)grid);
+    // 8-lane groups: the grid may be smaller than the record count the caller merges (block 0 writes empty records)
+    // CODA_B200_ASM=it1: one item per 8-lane group and iteration (fewer registers, three CTAs per SM) -- A/B knob
+    const char* asm_env = getenv("CODA_B200_ASM");
+    const bool it1 = asm_env && asm_env[0] == 'i' && asm_env[2] == '1';
+    int g8 = (int)min((long long)(N + 31) / 32, (long long)min(grid, coda_sm_count() * (it1 ? 3 : 2)));
     if (g8 < 1) g8 = 1;
     const size_t sm8 = (size_t)C * 4;
-#define LAUNCH_G8(K8) k_eig_assemble_g8<K8><<<g8, 256, sm8, st>>>(a, grid)
+#define LAUNCH_G8(K8)                                                         \
+  do {                                                                        \
+    if (it1) k_eig_assemble_g8<K8, 1><<<g8, 256, sm8, st>>>(a, grid);         \
+    else k_eig_assemble_g8<K8, 2><<<g8, 256, sm8, st>>>(a, grid);             \
+  } while (0)
     if (C <= 32) LAUNCH_G8(4);
     else if (C <= 64) LAUNCH_G8(8);
     else if (C <= 104) LAUNCH_G8(13);

@@ -457,9 +457,10 @@ class Engine:
             if self.pending:
                 self._cur().wait_event(self.ev_join)            # the class-t rows of the side stream
                 self.pending = False
-            self._call("coda_b200_template_gains", _ptr(self.ph_cache), self.H, self.C, _ptr(self.PB), _ptr(self.m0),
-                       _ptr(self.pi_hat), _ptr(self.gain), self._s())
-            if not self.fused_score:
+            if self.fused_score:
+                self._call("coda_b200_template_gains", _ptr(self.ph_cache), self.H, self.C, _ptr(self.PB), _ptr(self.m0),
+                           _ptr(self.pi_hat), _ptr(self.gain), self._s())
+            else:                                               # template rows + heavy rows in one stream
                 self._call("coda_b200_row_gains", _ptr(self.ph_cache), _ptr(self.row_cls), self.n_heavy, self.H, self.C,
                            _ptr(self.PB), _ptr(self.m0), _ptr(self.pi_hat), _ptr(self.gain), self._s())
         else:

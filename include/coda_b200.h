@@ -219,9 +219,10 @@ int coda_b200_gain_eig(const float* U, int64_t N, int C, int H, const int32_t* e
                        coda_stream_t stream);
 int coda_b200_ell_build(const int32_t* ent_off, const int32_t* ent_row, const uint16_t* ent_cls, int64_t N, int K,
                         int32_t* ell_row /*[N][K], -1 = empty*/, uint16_t* ell_cls /*[N][K]*/, coda_stream_t stream);
-/* gain[T + r] (coda.py:274-276) of the n_heavy heavy rows from their cached rows (ph_cache + T*Hp...), row_cls[r] =
- * class of heavy row r: the HBM-bound stream of the two-kernel scoring pass (row_gains, then gain_eig with
- * ph_cache == NULL).  Item-major rows make the per-item gains contiguous for the assembly that follows. */
+/* gain[r] (coda.py:274-276) of ALL T + n_heavy rows from their cached rows -- the template rows (class = r / (1+H))
+ * and the heavy rows (class = row_cls[r - T]) in one stream: the HBM-bound kernel of the two-kernel scoring pass
+ * (row_gains, then gain_eig with ph_cache == NULL).  Item-major heavy rows make the per-item gains contiguous for the
+ * assembly that follows. */
 int coda_b200_row_gains(const float* ph_cache, const uint16_t* row_cls, int64_t n_heavy, int H, int C,
                         const float* PB, const float* m0, const float* pi_hat, float* gain, coda_stream_t stream);
 

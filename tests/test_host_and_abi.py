@@ -259,3 +259,51 @@ def test_baseline_selectors_resolve_to_the_reference_when_pointed_at_it():
     env = dict(os.environ, PYTHONPATH=ROOT, CODA_REFERENCE_PATH=ref)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0 and "OK coda.baselines.iid" in r.stdout, r.stdout + r.stderr[-1500:]
+
+
+def test_best2_merge_matches_a_flat_scan_property():
+    """hypothesis: the (value, lowest index, runner-up value) records of csrc/common.cuh (host mirror dist.merge_best2)
+    merged over any partition equal one flat scan -- the runner-up is what lets the host-free loop flag an isclose tie."""
+    from hypothesis import given, settings, strategies as st
+    from coda_b200.dist import IDX_NONE, merge_best2
+
+    vals = st.sampled_from([0.0, 0.125, 0.25, 0.25, 0.5, 0.5])
+
+    @settings(max_examples=300, deadline=None)
+    @given(st.lists(vals, min_size=1, max_size=30), st.integers(1, 6), st.randoms())
+    def check(items, nshards, rnd):
+        def flat(idxs):
+            idxs = list(idxs)
+            if not idxs:
+                return (float("-inf"), IDX_NONE, float("-inf"))
+            best = max(idxs, key=lambda i: (items[i], -i))
+            rest = [items[i] for i in idxs if i != best]
+            return (items[best], best, max(rest) if rest else float("-inf"))
+        whole = flat(range(len(items)))
+        bounds = sorted(rnd.sample(range(len(items) + 1), min(nshards - 1, len(items) + 1)))
+        cuts = [0] + bounds + [len(items)]
+        shards = [flat(range(cuts[k], cuts[k + 1])) for k in range(len(cuts) - 1)]
+        rnd.shuffle(shards)
+        assert merge_best2(shards) == whole
+    check()
+
+
+def test_compact_slab_densify_and_generator():
+    from coda_b200 import CompactSlab
+    from coda_b200.synth import shard_range, synth_compact
+    ids, probs, labels = synth_compact(9, 500, 40, 4, seed=2)
+    slab = CompactSlab(ids, probs, 40)
+    dense = slab.densify()
+    assert dense.shape == (9, 500, 40) and torch.allclose(dense.sum(-1), torch.ones(9, 500), atol=1e-5)
+    assert float(dense.min()) >= 0 and torch.equal(dense.argmax(-1), ids[..., 0].long())
+    assert bool((probs[..., :-1] >= probs[..., 1:]).all())                       # descending scores
+    assert bool((dense.gather(2, ids.long()) == probs).all())                    # listed classes carry their scores
+    rest = dense.sum(-1) - probs.sum(-1)
+    assert bool((rest > 0).all())                                                 # some mass is always spread
+    # shard invariance of the generator and N-range views
+    parts = [synth_compact(9, 500, 40, 4, seed=2, n_lo=lo, n_hi=hi) for lo, hi in (shard_range(500, r, 3) for r in range(3))]
+    assert torch.equal(torch.cat([p[0] for p in parts], 1), ids) and torch.equal(torch.cat([p[1] for p in parts], 1), probs)
+    v = slab.narrow_items(100, 200)
+    assert v.shape == (9, 100, 40) and torch.equal(v.densify(), dense[:, 100:200])
+    with pytest.raises(TypeError):
+        CompactSlab(ids.long(), probs, 40)

@@ -504,9 +504,11 @@ def main():
 
     extra = {}
     extra_list = [x for x in args.extra_modes.split(",") if x and x != args.mode]
+    import gc
     for m in extra_list:                                        # other modes on the same slab, a few steps each
         sel.close()
         del sel, eng
+        gc.collect()
         torch.cuda.empty_cache()
         sel, t_i = make(ds, m)
         eng = sel.engine
@@ -518,7 +520,8 @@ def main():
     if args.dense_extra and not args.dense and world == 1 and not wl.get("compact"):
         # the dense worst case (wrong class uniform over all C) beside the default slab
         sel.close()
-        del sel, eng, ds
+        del sel, eng, ds, labels_dev
+        gc.collect()
         torch.cuda.empty_cache()
         ds2, lab2, _lh2, _ = dataset(True)
         sel, t_i = make(ds2, args.mode)

@@ -762,10 +762,14 @@ class Engine:
         return {"D": self.D, "U": self.U, "labeled": self.labeled, "pisum": self.pisum, "step_ctr": self.step_ctr}
 
     def close(self):
+        """Release the graphs, the mailbox and every device buffer of this shard (the object is unusable afterwards)."""
         self.graphs.clear()
         if self._mailbox is not None:
             self._mailbox.close()
             self._mailbox = None
+        for k, v in list(self.__dict__.items()):
+            if isinstance(v, torch.Tensor) or k in ("preds", "compact", "st", "xchg", "_labels_keep"):
+                setattr(self, k, None)
 
 
 def build_engines(shards, group, **kw):

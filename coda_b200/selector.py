@@ -424,5 +424,8 @@ class CODA(ModelSelector):
             random.setstate(sd["python_random_state"])
 
     def close(self):
+        """Free the device memory of every shard now (a selector is otherwise kept alive by reference cycles until gc)."""
         for e in self.engines:
             e.close()
+        self._labels_dev = None
+        self.dataset = None

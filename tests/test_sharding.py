@@ -198,3 +198,23 @@ def test_single_process_multi_gpu_front_end():
     loop = _mk(preds, labels, gpus=2)
     loop.run_steps(int(g["steps"]), labels)
     assert loop.history()[0].tolist() == [int(i) for i in g["idx"]]
+
+
+def test_sharded_file_dataset_feeds_the_selector(tmp_path):
+    """an (H, N, C) `.pt` slab on disk read through mmap, one N-range per shard (no shard ever
+    materialises the whole tensor), straight into the selector: the same run as from the in-memory tensor."""
+    from coda_b200 import CODA, ShardedFileDataset, TensorDataset
+    g = load_golden("traj_small_h32_n3000_c10")
+    preds, labels = golden_slab(g)
+    f = str(tmp_path / "task.pt")
+    torch.save(preds, f)
+    torch.save(labels, f.replace(".pt", "_labels.pt"))
+    whole = ShardedFileDataset(f, "cuda:0")
+    assert whole.preds.shape == preds.shape and whole.n_global == 3000
+    sel = CODA(whole)
+    sel.run_steps(int(g["steps"]), whole.labels)
+    assert sel.history()[0].tolist() == [int(i) for i in g["idx"]]
+    # one rank's range of a 3-way split: the loader hands over exactly that N-range, offsets in global item indices
+    part = ShardedFileDataset(f, "cuda:0", rank=1, world=3)
+    assert (part.n_offset, part.preds.shape[1], part.n_global) == (1000, 1000, 3000)
+    assert torch.equal(part.preds.cpu(), preds[:, 1000:2000])

@@ -30,6 +30,25 @@ import torch
 
 from . import _native as nat
 
+_CONST_SLOTS = {}          # device index -> set of constant-memory term-table slots in use (csrc/slab.cu c_terms_bank)
+_CONST_TERMS = 3584
+
+
+def _acquire_const_slot(dev_index, H):
+    per = (2 * H + 63) // 64 * 64
+    used = _CONST_SLOTS.setdefault(dev_index, set())
+    for s in range(_CONST_TERMS // per):
+        if s not in used:
+            used.add(s)
+            return s
+    return -1                  # every slot of this device is taken: the shared-memory copy of the list is used
+
+
+def _release_const_slot(dev_index, slot):
+    if slot is not None and slot >= 0:
+        _CONST_SLOTS.get(dev_index, set()).discard(slot)
+
+
 TIE_CAP = 256
 REP_WORDS = 12 + TIE_CAP + TIE_CAP // 2     # [flags | record (8) | tie hdr (2) | pad | tie idx | tie val]
 MODES = ("incremental", "recompute", "recompute_all")
@@ -110,6 +129,8 @@ class Engine:
         self.ev_fork, self.ev_join, self.ev_tables = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
         self.graphs = {}
         self.labels_ptr = None
+        # a private slot of the device's constant-memory term table (several selectors / shards may share a device)
+        self.const_slot = _acquire_const_slot(self.dev.index, H) if os.environ.get("CODA_B200_R1_CONST", "1") != "0" else -1
         with self._on():
             self._alloc_static()
 
@@ -514,7 +535,7 @@ class Engine:
         else:
             self._call("coda_b200_pi_rank1", _ptr(self.preds), _ptr(self.ens), H, N, C, _ptr(self.sel), self.lr,
                        self.fx_shift, _ptr(self.terms), _ptr(self.U), _ptr(self.pisum), _ptr(self.flags),
-                       4 if fork else 8, s)
+                       4 if fork else 8, self.const_slot, s)
         if fork:
             main.wait_event(self.ev_tables)     # the mixture needs PB[t]; the rows are awaited by the scoring pass
             self.pending = True
@@ -761,9 +782,17 @@ class Engine:
         un-normalised marginals they imply, the label mask and the device step counter."""
         return {"D": self.D, "U": self.U, "labeled": self.labeled, "pisum": self.pisum, "step_ctr": self.step_ctr}
 
+    def __del__(self):
+        try:
+            _release_const_slot(self.dev.index, getattr(self, "const_slot", -1))
+        except Exception:
+            pass
+
     def close(self):
         """Release the graphs, the mailbox and every device buffer of this shard (the object is unusable afterwards)."""
         self.graphs.clear()
+        _release_const_slot(self.dev.index, self.const_slot)
+        self.const_slot = -1
         if self._mailbox is not None:
             self._mailbox.close()
             self._mailbox = None

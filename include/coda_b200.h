@@ -134,9 +134,12 @@ int coda_b200_shadow_build(const float* preds, int64_t model_stride, int H, int6
  * pisum_fx was zeroed by the step kernel and is accumulated into (this shard's sums).  ctas_per_sm (1..8)
  * bounds the grid so a concurrent stream keeps SM resources.  U must be 16-byte aligned and followed by 16
  * readable bytes (C <= 128 takes a bulk-TMA pipeline that rounds the last tile's copy up). */
+/* const_slot: >= 0 = the caller owns that slot of the per-device constant-memory term table (slots hold 2H terms
+ * rounded up to 64; floor(3584 / that) slots exist; no two streams of one process may use the same slot of the same
+ * device concurrently) -- the gather list is then read through the constant cache; -1 = shared-memory copy. */
 int coda_b200_pi_rank1(const float* preds, const float* ens, int H, int64_t N, int C, const int64_t* sel, double lr,
                        int fx_shift, const int32_t* terms, float* U, int64_t* pisum_fx, uint32_t* flags,
-                       int ctas_per_sm, coda_stream_t stream);
+                       int ctas_per_sm, int const_slot, coda_stream_t stream);
 
 /* ---- compact slab (BASELINE.json configs[4]: M=1024, N=4e6, C=1000 is 16.4 TB dense; no reference counterpart --
  *      the reference cannot run there, coda.py:227 materialises a second slab) ----------------------------------

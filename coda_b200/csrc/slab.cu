@@ -657,7 +657,7 @@ __constant__ R1Term c_terms_bank[R1_CONST_TERMS];
 // GU: gathers in flight per lane, NR: U rows in flight per warp (more of both = more bytes in flight per SM at
 // the price of registers / resident warps)
 template <int KC, int GU = 16, int NR = 4, bool CONST_TERMS = false>
-__global__ void __launch_bounds__(256, (GU > 16 ? 3 : 1)) k_pi_rank1(const float* __restrict__ preds, const float* __restrict__ E,
+__global__ void __launch_bounds__(256, (GU > 16 ? 3 : 4)) k_pi_rank1(const float* __restrict__ preds, const float* __restrict__ E,
                                                   long long N, int C, const long long* __restrict__ sel,
                                                   const int32_t* __restrict__ hdr, const R1Term* __restrict__ gterms,
                                                   int const_base, float lr, float fxs,

@@ -286,11 +286,9 @@ __global__ void __launch_bounds__(256) k_row_gains(const float* __restrict__ row
                                                    long long nrows, long long T, int H, const float* __restrict__ PB,
                                                    const float* __restrict__ m0, const float* __restrict__ pi_hat,
                                                    float* __restrict__ gain, const int32_t* __restrict__ row_slot,
-                                                   float* __restrict__ gain_ell, const long long* __restrict__ skip_sel) {
+                                                   float* __restrict__ gain_ell) {
   constexpr int Hp = 128 * NQ;
   constexpr int CH = 32;   // rows per warp chunk
-  // skip_sel: the rows of class skip_sel[1] are being rewritten on another stream right now; row_gains_class does them
-  const int skip = skip_sel ? (int)skip_sel[1] : -1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float4 m[NQ], fm[NQ];
 #pragma unroll
@@ -325,7 +323,6 @@ __global__ void __launch_bounds__(256) k_row_gains(const float* __restrict__ row
         const long long r = i + j;
         if (r < p1) {
           const int c = __shfl_sync(CODA_FULL, mycls, (int)(r - p0));
-          if (c == skip) continue;
           const float pic = __ldg(pi_hat + c);
           const float4* pb = reinterpret_cast<const float4*>(PB + (size_t)c * Hp);
           float g = 0.f;
@@ -347,19 +344,10 @@ __global__ void __launch_bounds__(256) k_row_gains_any(const float* __restrict__
                                                        long long nrows, long long T, int H, int Hp, const float* __restrict__ PB,
                                                        const float* __restrict__ m0, const float* __restrict__ pi_hat,
                                                        float* __restrict__ gain, const int32_t* __restrict__ row_slot,
-                                                       float* __restrict__ gain_ell, const long long* __restrict__ skip_sel,
-                                                       const int32_t* __restrict__ row_of, const long long* __restrict__ cls_base) {
+                                                       float* __restrict__ gain_ell) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* m0s = reinterpret_cast<float*>(smem_raw);
   float* fm0 = m0s + Hp;
-  // two uses: the whole row range (row_of == NULL; rows of class skip_sel[1] skipped if given), or -- row_of given --
-  // exactly the work-list range of class skip_sel[1] (the rows another stream has just rewritten)
-  const int tcls = skip_sel ? (int)skip_sel[1] : -1;
-  long long q0 = 0;
-  if (row_of) {
-    q0 = cls_base[tcls];
-    nrows = cls_base[tcls + 1] - q0;
-  }
   for (int h = threadIdx.x; h < Hp; h += blockDim.x) {
     const float m = h < H ? m0[h] : 0.f;
     m0s[h] = m;
@@ -367,10 +355,8 @@ __global__ void __launch_bounds__(256) k_row_gains_any(const float* __restrict__
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (long long i = (long long)blockIdx.x * 8 + warp; i < nrows; i += (long long)gridDim.x * 8) {
-    const long long r = row_of ? (long long)row_of[q0 + i] : i;
-    const int c = row_of ? tcls : (r < T ? (int)(r / (1 + H)) : (int)row_cls[r - T]);
-    if (!row_of && c == tcls) continue;
+  for (long long r = (long long)blockIdx.x * 8 + warp; r < nrows; r += (long long)gridDim.x * 8) {
+    const int c = r < T ? (int)(r / (1 + H)) : (int)row_cls[r - T];
     const float pic = pi_hat[c];
     const float* row = rows + (size_t)r * Hp;
     const float* pb = PB + (size_t)c * Hp;
@@ -392,8 +378,7 @@ __global__ void __launch_bounds__(256) k_row_gains_any(const float* __restrict__
 
 extern "C" int coda_b200_row_gains(const float* ph_cache, const uint16_t* row_cls, int64_t n_heavy, int H, int C,
                                    const float* PB, const float* m0, const float* pi_hat, float* gain,
-                                   const int32_t* row_slot, float* gain_ell, const int64_t* skip_sel,
-                                   coda_stream_t stream) {
+                                   const int32_t* row_slot, float* gain_ell, coda_stream_t stream) {
   CODA_CHECK_ARG((row_slot == nullptr) == (gain_ell == nullptr), "row_gains: row_slot and gain_ell go together");
   CODA_CHECK_ARG(ph_cache && PB && m0 && pi_hat && gain && (row_cls || n_heavy == 0), "row_gains: null pointer");
   const int Hp = (H + 31) / 32 * 32;
@@ -405,8 +390,7 @@ extern "C" int coda_b200_row_gains(const float* ph_cache, const uint16_t* row_cl
   if (Hp % 128 == 0 && Hp <= 512) {
     int grid = (int)min((long long)(nrows + 255) / 256, (long long)coda_sm_count() * 6);
     if (grid < 1) grid = 1;
-  const long long* skp = reinterpret_cast<const long long*>(skip_sel);
-#define LAUNCH_RG(NQ) k_row_gains<NQ><<<grid, 256, 0, st>>>(rows, row_cls, nrows, T, H, PB, m0, pi_hat, g, row_slot, gain_ell, skp)
+#define LAUNCH_RG(NQ) k_row_gains<NQ><<<grid, 256, 0, st>>>(rows, row_cls, nrows, T, H, PB, m0, pi_hat, g, row_slot, gain_ell)
     if (Hp == 128) LAUNCH_RG(1);
     else if (Hp == 256) LAUNCH_RG(2);
     else if (Hp == 384) LAUNCH_RG(3);
@@ -417,27 +401,8 @@ extern "C" int coda_b200_row_gains(const float* ph_cache, const uint16_t* row_cl
   }
   int grid = (int)min((long long)(nrows + 7) / 8, (long long)coda_sm_count() * 8);
   if (grid < 1) grid = 1;
-  k_row_gains_any<<<grid, 256, (size_t)2 * Hp * 4, st>>>(rows, row_cls, nrows, T, H, Hp, PB, m0, pi_hat, g, row_slot, gain_ell,
-                                                         reinterpret_cast<const long long*>(skip_sel), nullptr, nullptr);
+  k_row_gains_any<<<grid, 256, (size_t)2 * Hp * 4, st>>>(rows, row_cls, nrows, T, H, Hp, PB, m0, pi_hat, g, row_slot, gain_ell);
   CODA_LAUNCH_OK("k_row_gains_any");
-  return CODA_B200_OK;
-}
-
-extern "C" int coda_b200_row_gains_class(const float* ph_cache, const int32_t* row_of, const int64_t* cls_base,
-                                         const int64_t* sel, int64_t max_class_rows, int H, int C, const float* PB,
-                                         const float* m0, const float* pi_hat, float* gain, const int32_t* row_slot,
-                                         float* gain_ell, coda_stream_t stream) {
-  CODA_CHECK_ARG(ph_cache && row_of && cls_base && sel && PB && m0 && pi_hat && gain, "row_gains_class: null pointer");
-  CODA_CHECK_ARG((row_slot == nullptr) == (gain_ell == nullptr), "row_gains_class: row_slot and gain_ell go together");
-  if (max_class_rows <= 0) return CODA_B200_OK;
-  const int Hp = (H + 31) / 32 * 32;
-  const long long T = (long long)C * (1 + H);
-  int grid = (int)min((long long)(max_class_rows + 7) / 8, (long long)coda_sm_count() * 8);
-  if (grid < 1) grid = 1;
-  k_row_gains_any<<<grid, 256, (size_t)2 * Hp * 4, as_stream(stream)>>>(
-      ph_cache, nullptr, 0, T, H, Hp, PB, m0, pi_hat, gain, row_slot, gain_ell, reinterpret_cast<const long long*>(sel), row_of,
-      reinterpret_cast<const long long*>(cls_base));
-  CODA_LAUNCH_OK("k_row_gains_any(class)");
   return CODA_B200_OK;
 }
 

@@ -121,8 +121,6 @@ class Engine:
         # CODA_B200_OVERLAP=0: class-t table / row refresh on the main stream instead of a side stream
         self.overlap = os.environ.get("CODA_B200_OVERLAP", "1") != "0"
         self.use_graph = os.environ.get("CODA_B200_GRAPH", "1") != "0"
-        # CODA_B200_SPLIT_GAINS=0: join the side stream before the gain stream instead of streaming around class t
-        self.split_gains = os.environ.get("CODA_B200_SPLIT_GAINS", "1") != "0"
         self.profile, self.profile_only = None, None
         self.xchg = None                                      # set by the group (dist.py) before the first exchange
         self._mailbox = None
@@ -350,7 +348,6 @@ class Engine:
         cls_base = np.zeros(C + 1, dtype=np.int64)
         np.cumsum(per_cls, out=cls_base[1:])
         self.npairs = int(cls_base[-1])                         # == T + n_heavy
-        self.max_cls_rows = int(per_cls.max())
         if self.npairs >= 2 ** 31 or n_ent >= 2 ** 31:
             raise NotImplementedError("coda_b200: more than 2^31 rows in one shard")
         self.ent_off = self._z((N + 1,), torch.int32)
@@ -391,9 +388,7 @@ class Engine:
             self.ell_k = (self.max_entries + 3) // 4 * 4
             self.ell_row = self._e((N, self.ell_k), torch.int32)
             self.ell_cls = self._e((N, self.ell_k), torch.int16)
-            # CODA_B200_GAIN_ELL=1: heavy-row gains also land in entry-list order (no dependent gather in the assembly).
-            # Measured slower (row_gains 0.72 -> 0.86 ms for the scattered 4-byte stores, assembly 0.21 -> 0.26 ms): off.
-            if self.mode == "incremental" and os.environ.get("CODA_B200_GAIN_ELL", "0") == "1":
+            if self.mode == "incremental":      # heavy-row gains land in entry-list order (no gather in the assembly)
                 self.row_slot = self._z((max(1, self.n_heavy),), torch.int32)
                 self.gain_ell = self._z((N, self.ell_k), torch.float32)
             self._call("coda_b200_ell_build", _ptr(self.ent_off), _ptr(self.ent_row), _ptr(self.ent_cls), N, self.ell_k,
@@ -483,25 +478,16 @@ class Engine:
             if not self.cache_valid:
                 self._pair_rows(0, self.ntiles, gains=False)    # fill the row cache once
                 self.cache_valid = True
-            split = self.pending and self.split_gains and not self.fused_score
-            if self.pending and not split:
+            if self.pending:
                 self._cur().wait_event(self.ev_join)            # the class-t rows of the side stream
                 self.pending = False
             if self.fused_score:
                 self._call("coda_b200_template_gains", _ptr(self.ph_cache), self.H, self.C, _ptr(self.PB), _ptr(self.m0),
                            _ptr(self.pi_hat), _ptr(self.gain), self._s())
             else:                                               # template rows + heavy rows in one stream
-                # `split`: the side stream is still rewriting the cached rows of class t -- stream every other class
-                # now, join, then do the few rows of class t
                 self._call("coda_b200_row_gains", _ptr(self.ph_cache), _ptr(self.row_cls), self.n_heavy, self.H, self.C,
                            _ptr(self.PB), _ptr(self.m0), _ptr(self.pi_hat), _ptr(self.gain), _ptr(self.row_slot),
-                           _ptr(self.gain_ell), _ptr(self.sel) if split else None, self._s())
-                if split:
-                    self._cur().wait_event(self.ev_join)
-                    self.pending = False
-                    self._call("coda_b200_row_gains_class", _ptr(self.ph_cache), _ptr(self.row_of), _ptr(self.cls_base),
-                               _ptr(self.sel), self.max_cls_rows, self.H, self.C, _ptr(self.PB), _ptr(self.m0),
-                               _ptr(self.pi_hat), _ptr(self.gain), _ptr(self.row_slot), _ptr(self.gain_ell), self._s())
+                           _ptr(self.gain_ell), self._s())
         else:
             if self.pending:
                 self._cur().wait_event(self.ev_join)

@@ -230,17 +230,9 @@ int coda_b200_ell_build(const int32_t* ent_off, const int32_t* ent_row, const ui
  * assembly that follows. */
 /* row_slot / gain_ell (optional, both or neither): every heavy row's gain is also stored at gain_ell[row_slot[r]], i.e.
  * in the order of its item's entry list, so the assembly reads it without a dependent gather. */
-/* skip_sel (optional, device {idx, class}): leave out the rows of class skip_sel[1] -- another stream is rewriting
- * their cached rows right now; coda_b200_row_gains_class does exactly those once it has finished. */
 int coda_b200_row_gains(const float* ph_cache, const uint16_t* row_cls, int64_t n_heavy, int H, int C,
                         const float* PB, const float* m0, const float* pi_hat, float* gain, const int32_t* row_slot,
-                        float* gain_ell, const int64_t* skip_sel, coda_stream_t stream);
-/* gain (+ gain_ell) of the rows of class sel[1] only: work-list positions cls_base[t]..cls_base[t+1] -> row_of.
- * max_class_rows sizes the grid (the class is only known on the device). */
-int coda_b200_row_gains_class(const float* ph_cache, const int32_t* row_of, const int64_t* cls_base, const int64_t* sel,
-                              int64_t max_class_rows, int H, int C, const float* PB, const float* m0,
-                              const float* pi_hat, float* gain, const int32_t* row_slot, float* gain_ell,
-                              coda_stream_t stream);
+                        float* gain_ell, coda_stream_t stream);
 
 /* ---- fused single-CTA step kernels: selection, label, posterior update, mixture --------------------------- */
 typedef struct coda_step { /* host struct: this shard's device state */

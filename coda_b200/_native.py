@@ -92,9 +92,9 @@ SIGNATURES = {
     "coda_b200_pair_rows_tc": (i32, [p, i32, i32, p, p, p, p, p, p, p, i32, p, p, p, p, p, p]),
     "coda_b200_template_gains": (i32, [p, i32, i32, p, p, p, p, p]),
     "coda_b200_eig_blocks": (i32, [i64, i32, i32]),
-    "coda_b200_gain_eig": (i32, [p, i64, i32, i32, p, p, p, p, p, p, p, p, p, p, p, i64, i32, p, p, i32, p, p, p, p, p]),
-    "coda_b200_ell_build": (i32, [p, p, p, i64, i32, i32, p, p, p, p]),
-    "coda_b200_row_gains": (i32, [p, p, i64, i32, i32, p, p, p, p, p, p, p]),
+    "coda_b200_gain_eig": (i32, [p, i64, i32, i32, p, p, p, p, p, p, p, p, p, p, p, i64, i32, p, p, i32, p, p, p, p]),
+    "coda_b200_ell_build": (i32, [p, p, p, i64, i32, p, p, p]),
+    "coda_b200_row_gains": (i32, [p, p, i64, i32, i32, p, p, p, p, p]),
     "coda_b200_step_select": (i32, [PS, PX, p]),
     "coda_b200_step_merge": (i32, [PS, PX, p]),
     "coda_b200_step_label": (i32, [PS, PX, p]),

@@ -40,7 +40,6 @@ struct GainEigArgs {
   const int32_t* ell_row;     // optional ELL copy of the entry lists: [N][ell_k] row ids (-1 = empty) ...
   const uint16_t* ell_cls;    // ... and classes
   int ell_k;
-  const float* gain_ell;      // optional [N][ell_k]: the heavy rows' gains in entry-list order (written by row_gains)
 };
 
 __device__ __forceinline__ float gain4(const float4 ph, const float4 pb, const float4 m, const float4 fm, float pic) {
@@ -285,8 +284,7 @@ template <int NQ>
 __global__ void __launch_bounds__(256) k_row_gains(const float* __restrict__ rows, const uint16_t* __restrict__ row_cls,
                                                    long long nrows, long long T, int H, const float* __restrict__ PB,
                                                    const float* __restrict__ m0, const float* __restrict__ pi_hat,
-                                                   float* __restrict__ gain, const int32_t* __restrict__ row_slot,
-                                                   float* __restrict__ gain_ell) {
+                                                   float* __restrict__ gain) {
   constexpr int Hp = 128 * NQ;
   constexpr int CH = 32;   // rows per warp chunk
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -329,10 +327,7 @@ __global__ void __launch_bounds__(256) k_row_gains(const float* __restrict__ row
 #pragma unroll
           for (int q = 0; q < NQ; ++q) g += gain4(a[j][q], __ldg(pb + q * 32 + lane), m[q], fm[q], pic);
           g = warp_sum(g);
-          if (lane == 0) {
-            gain[r] = g;
-            if (row_slot && r >= T) gain_ell[row_slot[r - T]] = g;   // the same gain where the item's entry list expects it
-          }
+          if (lane == 0) gain[r] = g;
         }
       }
     }
@@ -343,8 +338,7 @@ __global__ void __launch_bounds__(256) k_row_gains(const float* __restrict__ row
 __global__ void __launch_bounds__(256) k_row_gains_any(const float* __restrict__ rows, const uint16_t* __restrict__ row_cls,
                                                        long long nrows, long long T, int H, int Hp, const float* __restrict__ PB,
                                                        const float* __restrict__ m0, const float* __restrict__ pi_hat,
-                                                       float* __restrict__ gain, const int32_t* __restrict__ row_slot,
-                                                       float* __restrict__ gain_ell) {
+                                                       float* __restrict__ gain) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* m0s = reinterpret_cast<float*>(smem_raw);
   float* fm0 = m0s + Hp;
@@ -369,17 +363,13 @@ __global__ void __launch_bounds__(256) k_row_gains_any(const float* __restrict__
       g += gain4(ph, p4, m4, f4, pic);
     }
     g = warp_sum(g);
-    if (lane == 0) {
-      gain[r] = g;
-      if (row_slot && r >= T) gain_ell[row_slot[r - T]] = g;
-    }
+    if (lane == 0) gain[r] = g;
   }
 }
 
 extern "C" int coda_b200_row_gains(const float* ph_cache, const uint16_t* row_cls, int64_t n_heavy, int H, int C,
                                    const float* PB, const float* m0, const float* pi_hat, float* gain,
-                                   const int32_t* row_slot, float* gain_ell, coda_stream_t stream) {
-  CODA_CHECK_ARG((row_slot == nullptr) == (gain_ell == nullptr), "row_gains: row_slot and gain_ell go together");
+                                   coda_stream_t stream) {
   CODA_CHECK_ARG(ph_cache && PB && m0 && pi_hat && gain && (row_cls || n_heavy == 0), "row_gains: null pointer");
   const int Hp = (H + 31) / 32 * 32;
   const long long T = (long long)C * (1 + H);
@@ -390,7 +380,7 @@ extern "C" int coda_b200_row_gains(const float* ph_cache, const uint16_t* row_cl
   if (Hp % 128 == 0 && Hp <= 512) {
     int grid = (int)min((long long)(nrows + 255) / 256, (long long)coda_sm_count() * 6);
     if (grid < 1) grid = 1;
-#define LAUNCH_RG(NQ) k_row_gains<NQ><<<grid, 256, 0, st>>>(rows, row_cls, nrows, T, H, PB, m0, pi_hat, g, row_slot, gain_ell)
+#define LAUNCH_RG(NQ) k_row_gains<NQ><<<grid, 256, 0, st>>>(rows, row_cls, nrows, T, H, PB, m0, pi_hat, g)
     if (Hp == 128) LAUNCH_RG(1);
     else if (Hp == 256) LAUNCH_RG(2);
     else if (Hp == 384) LAUNCH_RG(3);
@@ -401,7 +391,7 @@ extern "C" int coda_b200_row_gains(const float* ph_cache, const uint16_t* row_cl
   }
   int grid = (int)min((long long)(nrows + 7) / 8, (long long)coda_sm_count() * 8);
   if (grid < 1) grid = 1;
-  k_row_gains_any<<<grid, 256, (size_t)2 * Hp * 4, st>>>(rows, row_cls, nrows, T, H, Hp, PB, m0, pi_hat, g, row_slot, gain_ell);
+  k_row_gains_any<<<grid, 256, (size_t)2 * Hp * 4, st>>>(rows, row_cls, nrows, T, H, Hp, PB, m0, pi_hat, g);
   CODA_LAUNCH_OK("k_row_gains_any");
   return CODA_B200_OK;
 }
@@ -439,7 +429,6 @@ __global__ void __launch_bounds__(256, (IT8 == 1 ? 3 : 2)) k_eig_assemble_g8(Gai
     }
     float u[IT8][KC8];
     int er[IT8][4], ec[IT8][4];
-    float ge[IT8][4];
 #pragma unroll
     for (int i = 0; i < IT8; ++i) {
       const long long n = min(nb + i, a.N - 1);
@@ -453,12 +442,10 @@ __global__ void __launch_bounds__(256, (IT8 == 1 ? 3 : 2)) k_eig_assemble_g8(Gai
       for (int j = 0; j < 4; ++j) {
         const int e = g + 8 * j;
         er[i][j] = -1; ec[i][j] = 0;
-        ge[i][j] = 0.f;
         if (a.ell_row) {     // the entry address follows from the item index: one dependent load level less
           if (e < a.ell_k) {
             er[i][j] = __ldg(a.ell_row + (size_t)n * a.ell_k + e);
             ec[i][j] = __ldg(a.ell_cls + (size_t)n * a.ell_k + e);
-            if (a.gain_ell) ge[i][j] = __ldg(a.gain_ell + (size_t)n * a.ell_k + e);   // heavy gains: no dependent gather
           }
         } else if (e < ne[i]) {
           er[i][j] = __ldg(a.ent_row + e0[i] + e);
@@ -474,7 +461,7 @@ __global__ void __launch_bounds__(256, (IT8 == 1 ? 3 : 2)) k_eig_assemble_g8(Gai
       for (int j = 0; j < 4; ++j) {
         eg[i][j] = 0.f; eu[i][j] = 0.f;
         if (er[i][j] >= 0) {
-          eg[i][j] = (a.gain_ell && er[i][j] >= a.T) ? ge[i][j] : __ldg(a.gain + er[i][j]);   // template gains: a 100 KB table
+          eg[i][j] = __ldg(a.gain + er[i][j]);
           eu[i][j] = __ldg(a.U + (size_t)n * C + ec[i][j]);
         }
       }
@@ -556,8 +543,7 @@ extern "C" int coda_b200_gain_eig(const float* U, int64_t N, int C, int H, const
                                   const float* ph_cache, const float* gain, const float* PB, const float* m0,
                                   const float* pi_hat, const uint8_t* labeled, const uint8_t* disagree,
                                   int64_t n_offset, int max_entries, const int32_t* ell_row, const uint16_t* ell_cls,
-                                  int ell_k, const float* gain_ell, float* eig, int64_t* partials, uint32_t* flags,
-                                  coda_stream_t stream) {
+                                  int ell_k, float* eig, int64_t* partials, uint32_t* flags, coda_stream_t stream) {
   CODA_CHECK_ARG(U && ent_off && heavy_off && ent_row && ent_cls && gain && PB && m0 && pi_hat && labeled && disagree &&
                      eig && partials && flags,
                  "gain_eig: null pointer");
@@ -570,7 +556,6 @@ extern "C" int coda_b200_gain_eig(const float* U, int64_t N, int C, int H, const
   a.partials = reinterpret_cast<long long*>(partials); a.flags = flags;
   a.ell_row = (ell_row && ell_cls && ell_k >= 1 && ell_k <= 32) ? ell_row : nullptr;
   a.ell_cls = ell_cls; a.ell_k = ell_k;
-  a.gain_ell = a.ell_row ? gain_ell : nullptr;
   const bool from_cache = ph_cache != nullptr;
   const int nq = !from_cache ? 0 : ((a.Hp == 128) ? 1 : (a.Hp == 256 ? 2 : 0));   // NQ = 0: m0 / f(m0) copies in shared memory
   const int kc = C <= 32 ? 1 : (C <= 64 ? 2 : (C <= 128 ? 4 : 0));
@@ -674,28 +659,23 @@ extern "C" int coda_b200_template_gains(const float* ph_cache, int H, int C, con
 
 // ELL copy of the per-item entry lists for the 8-lane assembly: ell_row[n][k] = row id or -1, ell_cls[n][k] = class.
 __global__ void k_ell_build(const int32_t* __restrict__ ent_off, const int32_t* __restrict__ ent_row,
-                            const uint16_t* __restrict__ ent_cls, long long N, int K, int T, int32_t* __restrict__ ell_row,
-                            uint16_t* __restrict__ ell_cls, int32_t* __restrict__ row_slot) {
+                            const uint16_t* __restrict__ ent_cls, long long N, int K, int32_t* __restrict__ ell_row,
+                            uint16_t* __restrict__ ell_cls) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N * K) return;
   const long long n = i / K;
   const int k = (int)(i % K);
   const int o = ent_off[n] + k;
   const bool has = o < ent_off[n + 1];
-  const int row = has ? ent_row[o] : -1;
-  ell_row[i] = row;
+  ell_row[i] = has ? ent_row[o] : -1;
   ell_cls[i] = has ? ent_cls[o] : (uint16_t)0;
-  if (row_slot && row >= T) row_slot[row - T] = (int32_t)i;      // where row_gains drops this heavy row's gain
 }
 
 extern "C" int coda_b200_ell_build(const int32_t* ent_off, const int32_t* ent_row, const uint16_t* ent_cls, int64_t N,
-                                   int K, int T, int32_t* ell_row, uint16_t* ell_cls, int32_t* row_slot,
-                                   coda_stream_t stream) {
+                                   int K, int32_t* ell_row, uint16_t* ell_cls, coda_stream_t stream) {
   CODA_CHECK_ARG(ent_off && ent_row && ent_cls && ell_row && ell_cls && K >= 1 && K <= 32, "ell_build: bad arguments");
-  CODA_CHECK_ARG((long long)N * K < (1ll << 31), "ell_build: N * K does not fit 32-bit slots");
   const long long tot = (long long)N * K;
-  k_ell_build<<<(unsigned)((tot + 255) / 256), 256, 0, as_stream(stream)>>>(ent_off, ent_row, ent_cls, N, K, T, ell_row,
-                                                                            ell_cls, row_slot);
+  k_ell_build<<<(unsigned)((tot + 255) / 256), 256, 0, as_stream(stream)>>>(ent_off, ent_row, ent_cls, N, K, ell_row, ell_cls);
   CODA_LAUNCH_OK("k_ell_build");
   return CODA_B200_OK;
 }

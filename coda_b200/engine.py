@@ -383,16 +383,13 @@ class Engine:
                    _ptr(self.cls_base), _ptr(cursor), _ptr(self.ent_row), _ptr(self.ent_cls), _ptr(self.zmask),
                    _ptr(self.row_of), _ptr(self.row_cls), s, n=2)
         # ELL copy of the entry lists when the longest one fits four entries per lane of an 8-lane group
-        self.ell_row, self.ell_cls, self.ell_k, self.row_slot, self.gain_ell = None, None, 0, None, None
-        if 0 < self.max_entries <= 32 and C <= 128 and N * ((self.max_entries + 3) // 4 * 4) < 2 ** 31:
+        self.ell_row, self.ell_cls, self.ell_k = None, None, 0
+        if 0 < self.max_entries <= 32 and C <= 128:
             self.ell_k = (self.max_entries + 3) // 4 * 4
             self.ell_row = self._e((N, self.ell_k), torch.int32)
             self.ell_cls = self._e((N, self.ell_k), torch.int16)
-            if self.mode == "incremental":      # heavy-row gains land in entry-list order (no gather in the assembly)
-                self.row_slot = self._z((max(1, self.n_heavy),), torch.int32)
-                self.gain_ell = self._z((N, self.ell_k), torch.float32)
             self._call("coda_b200_ell_build", _ptr(self.ent_off), _ptr(self.ent_row), _ptr(self.ent_cls), N, self.ell_k,
-                       T, _ptr(self.ell_row), _ptr(self.ell_cls), _ptr(self.row_slot), s)
+                       _ptr(self.ell_row), _ptr(self.ell_cls), s)
         self.gain = self._z((self.npairs,), torch.float32)      # information gain of every row (templates first)
         # CODA_B200_FUSED_SCORE=1: one kernel computes the row gains and assembles the per-item EIG (measured slower
         # than the streaming row-gain kernel followed by the 8-lane assembly)
@@ -486,8 +483,7 @@ class Engine:
                            _ptr(self.pi_hat), _ptr(self.gain), self._s())
             else:                                               # template rows + heavy rows in one stream
                 self._call("coda_b200_row_gains", _ptr(self.ph_cache), _ptr(self.row_cls), self.n_heavy, self.H, self.C,
-                           _ptr(self.PB), _ptr(self.m0), _ptr(self.pi_hat), _ptr(self.gain), _ptr(self.row_slot),
-                           _ptr(self.gain_ell), self._s())
+                           _ptr(self.PB), _ptr(self.m0), _ptr(self.pi_hat), _ptr(self.gain), self._s())
         else:
             if self.pending:
                 self._cur().wait_event(self.ev_join)
@@ -497,8 +493,7 @@ class Engine:
                    _ptr(self.ent_row), _ptr(self.ent_cls), _ptr(self.ph_cache) if self.fused_score else None,
                    _ptr(self.gain), _ptr(self.PB), _ptr(self.m0), _ptr(self.pi_hat), _ptr(self.labeled),
                    _ptr(self.disagree), self.n_offset, self.max_entries, _ptr(self.ell_row), _ptr(self.ell_cls),
-                   self.ell_k, _ptr(self.gain_ell) if (self.mode == "incremental" and not self.fused_score) else None,
-                   _ptr(self.eig), _ptr(self.partials), _ptr(self.flags), self._s())
+                   self.ell_k, _ptr(self.eig), _ptr(self.partials), _ptr(self.flags), self._s())
         self.scored = True
 
     def _post_label(self):

@@ -218,21 +218,16 @@ int coda_b200_gain_eig(const float* U, int64_t N, int C, int H, const int32_t* e
                        const int32_t* ent_row, const uint16_t* ent_cls, const float* ph_cache, const float* gain,
                        const float* PB, const float* m0, const float* pi_hat, const uint8_t* labeled,
                        const uint8_t* disagree, int64_t n_offset, int max_entries, const int32_t* ell_row,
-                       const uint16_t* ell_cls, int ell_k, const float* gain_ell /*optional [N][ell_k], see row_gains*/,
-                       float* eig, int64_t* partials, uint32_t* flags, coda_stream_t stream);
-/* row_slot (optional) [n_heavy]: position n*K + k of every heavy row in the ELL copy (T = C*(1+H)). */
+                       const uint16_t* ell_cls, int ell_k, float* eig, int64_t* partials, uint32_t* flags,
+                       coda_stream_t stream);
 int coda_b200_ell_build(const int32_t* ent_off, const int32_t* ent_row, const uint16_t* ent_cls, int64_t N, int K,
-                        int T, int32_t* ell_row /*[N][K], -1 = empty*/, uint16_t* ell_cls /*[N][K]*/,
-                        int32_t* row_slot, coda_stream_t stream);
+                        int32_t* ell_row /*[N][K], -1 = empty*/, uint16_t* ell_cls /*[N][K]*/, coda_stream_t stream);
 /* gain[r] (coda.py:274-276) of ALL T + n_heavy rows from their cached rows -- the template rows (class = r / (1+H))
  * and the heavy rows (class = row_cls[r - T]) in one stream: the HBM-bound kernel of the two-kernel scoring pass
  * (row_gains, then gain_eig with ph_cache == NULL).  Item-major heavy rows make the per-item gains contiguous for the
  * assembly that follows. */
-/* row_slot / gain_ell (optional, both or neither): every heavy row's gain is also stored at gain_ell[row_slot[r]], i.e.
- * in the order of its item's entry list, so the assembly reads it without a dependent gather. */
 int coda_b200_row_gains(const float* ph_cache, const uint16_t* row_cls, int64_t n_heavy, int H, int C,
-                        const float* PB, const float* m0, const float* pi_hat, float* gain, const int32_t* row_slot,
-                        float* gain_ell, coda_stream_t stream);
+                        const float* PB, const float* m0, const float* pi_hat, float* gain, coda_stream_t stream);
 
 /* ---- fused single-CTA step kernels: selection, label, posterior update, mixture --------------------------- */
 typedef struct coda_step { /* host struct: this shard's device state */

@@ -382,6 +382,7 @@ def main():
         sel.run_steps(max(warm, 2), labels_dev)            # warm-up (>= 2: the first step is eager, then the capture)
         barrier()
         launches0 = eng.counters["launches"]
+        wait0 = eng._mailbox.epoch[4:8].clone() if eng._mailbox is not None else None
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         sel.run_steps(steps, labels_dev)
@@ -389,6 +390,9 @@ def main():
         barrier()
         ms = max_over_ranks(e0.elapsed_time(e1))
         eng.check_flags(sync=True)
+        if wait0 is not None:    # time the step kernels spent waiting for the peers' contributions (latency + skew), this rank
+            w = (eng._mailbox.epoch[4:8] - wait0).cpu().tolist()
+            graph_loop.exchange = {"argmax_record_ms_per_step": w[0] / 1e6 / steps, "marginal_sums_ms_per_step": w[1] / 1e6 / steps}
         return ms, eng.counters["launches"] - launches0
 
     def eager_profile(sel, labels_dev, steps):
@@ -471,7 +475,9 @@ def main():
     sel, t_init = make(ds, args.mode)
     eng = sel.engine
     sampler = ClockSampler(local_rank) if rank == 0 else None
+    graph_loop.exchange = None
     ms, launches = graph_loop(sel, labels_dev, args.warmup, args.steps)
+    exchange = graph_loop.exchange
     value = args.steps / (ms / 1e3)
     picks_dev = sel.history()[0][-(args.steps):].tolist()
     ties_dev = int(sel.history()[2].sum())
@@ -559,6 +565,7 @@ def main():
             "gpu_launches": launches,
             "roofline": roof,
             "kernel_ms": kernels,
+            "exchange_wait": exchange,
             "modes": extra,
             "cpu_baseline": cpu,
             "first_picks": {"device_loop": picks_dev[:8], "api": [p[0] for p in picks_api[:8]]},

@@ -23,7 +23,7 @@
 struct XchgView {
   int world, rank;
   unsigned char* box[CODA_B200_MAX_WORLD];
-  unsigned long long* epoch;             // [XCH_NCHAN]
+  unsigned long long* epoch;             // [2 * XCH_NCHAN]: epoch counters, then nanoseconds spent waiting, per channel
   uint32_t chan_off[XCH_NCHAN];
   uint32_t slot_bytes[XCH_NCHAN];
 };
@@ -80,9 +80,11 @@ __device__ __forceinline__ void xch_push(const XchgView& x, int ch, unsigned lon
   __syncthreads();
   if ((int)threadIdx.x < x.world) st_release_sys(xch_flag(x, threadIdx.x, ch, par, x.rank), ep);
 }
-// returns (to every thread) false if some peer did not arrive within 2 s
+// returns (to every thread) false if some peer did not arrive within 2 s.  The time thread 0 spends here (until the
+// slowest peer's contribution has landed: exchange latency + skew between the shards) is added to epoch[4 + ch] (ns).
 __device__ __forceinline__ bool xch_wait(const XchgView& x, int ch, unsigned long long ep) {
   __shared__ int s_ok;
+  const unsigned long long t_enter = globaltimer_ns();
   if (threadIdx.x == 0) s_ok = 1;
   __syncthreads();
   if ((int)threadIdx.x < x.world) {
@@ -96,6 +98,7 @@ __device__ __forceinline__ bool xch_wait(const XchgView& x, int ch, unsigned lon
     if (!ok) s_ok = 0;
   }
   __syncthreads();
+  if (threadIdx.x == 0) x.epoch[XCH_NCHAN + ch] += globaltimer_ns() - t_enter;
   return s_ok != 0;
 }
 __device__ __forceinline__ const unsigned char* xch_data(const XchgView& x, int ch, unsigned long long ep, int src) {

@@ -95,7 +95,7 @@ class Mailbox:
         with torch.cuda.device(self.device):
             nat.check(self.lib.coda_b200_xchg_alloc(self.bytes, ct.byref(ptr)), "xchg_alloc")
         self.ptr = int(ptr.value)
-        self.epoch = torch.zeros(4, dtype=torch.int64, device=self.device)
+        self.epoch = torch.zeros(8, dtype=torch.int64, device=self.device)     # epochs [0..4), wait ns [4..8)
         torch.cuda.synchronize(self.device)     # the zero fill ran on the current stream; shards may use their own
         self.opened = []
 

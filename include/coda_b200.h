@@ -72,7 +72,8 @@ int coda_b200_set_l2_fetch_granularity(int bytes);
 typedef struct coda_xchg { /* host struct */
   int world, rank;
   void* box[CODA_B200_MAX_WORLD]; /* mailbox of every rank as addressable from THIS rank's device; box[rank] is local */
-  uint64_t* epoch;                /* local, [4]: per-channel epoch counters (zero-initialised) */
+  uint64_t* epoch;                /* local, [8], zero-initialised: per-channel epoch counters [0..4) and the nanoseconds
+                                     spent waiting for peers per channel [4..8) (latency + skew; bench.py prints them) */
   int H, C, rep_words;            /* fix the slot sizes (same on every rank); rep_words: int64 words of a report block */
 } coda_xchg_t;
 size_t coda_b200_xchg_box_bytes(int world, int H, int C, int rep_words);

@@ -25,7 +25,7 @@ for k in range(6):
     print("   jvec eq", [torch.equal(e.jvec, one.engine.jvec) for e in many.engines], "hdr", one.engine.terms[:2].tolist(),
           [e.terms[:2].tolist() for e in many.engines], "sel", one.engine.sel.tolist(), [e.sel.tolist() for e in many.engines])
     ps = sum(e.pisum.cpu() for e in many.engines)
-    print("   pisum sum eq", torch.equal(ps, one.engine.pisum.cpu()), "epochs", [e._mailbox.epoch.tolist() for e in many.engines])
+    print("   pisum sum eq", torch.equal(ps, one.engine.pisum.cpu()), "epochs", [e._mailbox.epoch[:4].tolist() for e in many.engines])
     if not torch.equal(U1, Um):
         bad = (U1 != Um).any(1).nonzero().flatten()
         print("   first bad rows", bad[:10].tolist(), "cols", (U1 != Um).any(0).nonzero().flatten().tolist())

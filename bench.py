@@ -285,6 +285,15 @@ HOT = {   # C-ABI entry point -> kernel name printed in the roofline line
 }
 
 
+def gathered_models(eng):
+    """Models in the rank-1 gather list of the last step (two terms per model with the majority shortcut)."""
+    try:
+        nt, tp = (int(x) for x in eng.terms[:2].tolist())
+        return max(1, nt // 2 if tp >= 0 else nt)
+    except Exception:
+        return eng.H
+
+
 def algorithmic_bytes(eng):
     """Algorithmic bytes per launch, per shard."""
     H, N, C, Hp = eng.H, eng.N, eng.C, eng.Hp
@@ -296,7 +305,9 @@ def algorithmic_bytes(eng):
         # U rows + entry lists + one gain per entry + candidate masks; writes eig
         "coda_b200_gain_eig": ((4 * heavy * Hp) if getattr(eng, "fused_score", False) else 0) + 4 * N * C + lists + 4 * ent
                               + 2 * N + 4 * N,
-        "coda_b200_pi_rank1_compact": 24 * H * N + 4 * N * C + 8 * N,
+        # one 24-byte entry per gathered model and item (the models that disagree with the majority on the labeled item;
+        # read from the gather list of the last step) + the U row pass + the ensemble column
+        "coda_b200_pi_rank1_compact": 6 * getattr(eng, "K", 4) * gathered_models(eng) * N + 4 * N * C + 8 * N,
         # one float per (model, item) + the U row pass (read all, write one column) + the ensemble column
         "coda_b200_pi_rank1": 4 * H * N + 4 * N * C + 4 * N + 4 * N,
         "coda_b200_pi_full": 4 * H * N * C + 4 * N * C,

@@ -190,22 +190,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_pair_rows_tc(TcArgs a, int ti
   const uint32_t bytesB = 4u * tabB;
 
   // ---- phase A: logD = Z . dL (3 limbs) --------------------------------------------------------
-  if (tid == 0) {
+  // Two elected threads: tid 32 streams the operand chunks (it only ever waits for a stage to be released), tid 0 issues
+  // the MMAs (it only ever waits for a stage to be filled) -- so the tensor pipe is never held up by a TMA issue
+  // waiting for the previous chunk's MMAs to retire, and all STAGES_A stages are in flight.
+  if (tid == 32) {
     const unsigned char* src = reinterpret_cast<const unsigned char*>(a.dLb) + (size_t)c * nka * bytesA;
-    const uint32_t idesc = instr_desc_bf16(TC_NODES);
-    for (int kc = 0; kc < STAGES_A - 1 && kc < nka; ++kc) {
-      mbar_expect_tx(&fullA[kc], bytesA);
-      tma_load_1d(stgA + (size_t)kc * 48 * 1024, src + (size_t)kc * bytesA, bytesA, &fullA[kc]);
-    }
     for (int kc = 0; kc < nka; ++kc) {
       const int s = kc % STAGES_A;
-      const int kn = kc + STAGES_A - 1;
-      if (kn < nka) {
-        const int s1 = kn % STAGES_A;
-        if (kn >= STAGES_A) mbar_wait(&emptyA[s1], ((kn / STAGES_A) - 1) & 1);
-        mbar_expect_tx(&fullA[s1], bytesA);
-        tma_load_1d(stgA + (size_t)s1 * 48 * 1024, src + (size_t)kn * bytesA, bytesA, &fullA[s1]);
-      }
+      if (kc >= STAGES_A) mbar_wait(&emptyA[s], ((kc / STAGES_A) - 1) & 1);
+      mbar_expect_tx(&fullA[s], bytesA);
+      tma_load_1d(stgA + (size_t)s * 48 * 1024, src + (size_t)kc * bytesA, bytesA, &fullA[s]);
+    }
+    // prefetch the first phase-B stages while the epilogue below runs (their smem region is free once the
+    // phase-A MMAs have completed, which doneA certifies)
+    mbar_wait(doneA, 0);
+    const unsigned char* srcB = reinterpret_cast<const unsigned char*>(a.Gb) + (size_t)c * nkb * bytesB;
+    for (int kc = 0; kc < STAGES_B && kc < nkb; ++kc) {
+      mbar_expect_tx(&fullB[kc], bytesB);
+      tma_load_1d(stg + (size_t)kc * 32 * 1024, srcB + (size_t)kc * bytesB, bytesB, &fullB[kc]);
+    }
+  }
+  if (tid == 0) {
+    const uint32_t idesc = instr_desc_bf16(TC_NODES);
+    for (int kc = 0; kc < nka; ++kc) {
+      const int s = kc % STAGES_A;
       mbar_wait(&fullA[s], (kc / STAGES_A) & 1);
       tc_fence_after();
 #pragma unroll
@@ -224,14 +232,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_pair_rows_tc(TcArgs a, int ti
       mma_commit(&emptyA[s]);
     }
     mma_commit(doneA);
-    // prefetch the first phase-B stages while the epilogue below runs (their smem region is free once the
-    // phase-A MMAs have completed, which doneA certifies)
-    mbar_wait(doneA, 0);
-    const unsigned char* srcB = reinterpret_cast<const unsigned char*>(a.Gb) + (size_t)c * nkb * bytesB;
-    for (int kc = 0; kc < STAGES_B - 1 && kc < nkb; ++kc) {
-      mbar_expect_tx(&fullB[kc], bytesB);
-      tma_load_1d(stg + (size_t)kc * 32 * 1024, srcB + (size_t)kc * bytesB, bytesB, &fullB[kc]);
-    }
   }
   __syncwarp();
   mbar_wait(doneA, 0);
@@ -268,19 +268,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_pair_rows_tc(TcArgs a, int ti
   tc_fence_after();
 
   // ---- phase B: prob_k = D . G_k -----------------------------------------------------------------
-  if (tid == 0) {
+  if (tid == 32) {                                // the chunks beyond the STAGES_B prefetched above
     const unsigned char* srcB = reinterpret_cast<const unsigned char*>(a.Gb) + (size_t)c * nkb * bytesB;
+    for (int kc = STAGES_B; kc < nkb; ++kc) {
+      const int s = kc % STAGES_B;
+      mbar_wait(&emptyB[s], ((kc / STAGES_B) - 1) & 1);
+      mbar_expect_tx(&fullB[s], bytesB);
+      tma_load_1d(stg + (size_t)s * 32 * 1024, srcB + (size_t)kc * bytesB, bytesB, &fullB[s]);
+    }
+  }
+  if (tid == 0) {
     const uint32_t idesc = instr_desc_bf16(Hp);
     const uint32_t lboB = (uint32_t)(Hp / 8) * 128;
     for (int kc = 0; kc < nkb; ++kc) {
       const int s = kc % STAGES_B;
-      const int kn = kc + STAGES_B - 1;          // chunk to prefetch now
-      if (kn < nkb) {
-        const int sn = kn % STAGES_B;
-        if (kn >= STAGES_B) mbar_wait(&emptyB[sn], ((kn / STAGES_B) - 1) & 1);
-        mbar_expect_tx(&fullB[sn], bytesB);
-        tma_load_1d(stg + (size_t)sn * 32 * 1024, srcB + (size_t)kn * bytesB, bytesB, &fullB[sn]);
-      }
       mbar_wait(&fullB[s], (kc / STAGES_B) & 1);
       tc_fence_after();
       const uint64_t ahi = smem_desc(opA_s + (uint32_t)(kc * 2) * (TC_M / 8) * 128, (TC_M / 8) * 128, 128);

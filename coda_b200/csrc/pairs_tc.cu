@@ -25,7 +25,8 @@ constexpr int TC_NODES = 256;    // quadrature nodes
 constexpr int KA = 32;           // models per phase-A chunk
 constexpr int KB = 16;           // nodes per phase-B chunk
 constexpr int STAGES_A = 3;
-constexpr int TC_THREADS = 256;   // warps 0-3: columns [0, half), warps 4-7: columns [half, end) of their TMEM lane quadrant
+constexpr int TC_THREADS = 512;   // 16 warps: warp w works on TMEM lane quadrant w % 4 (hardware rule) and column part w / 4
+constexpr int TC_PARTS = TC_THREADS / 128;
 constexpr int STAGES_B = 3;
 
 struct TcArgs {
@@ -108,7 +109,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_pair_rows_tc(TcArgs a, int ti
   extern __shared__ __align__(1024) unsigned char smem[];
   const int H = a.H, Hp = a.Hp, W = a.W;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int quad = warp & 3, half = warp >> 2;      // TMEM lane quadrant (hardware: warp % 4), column half
+  const int quad = warp & 3, half = warp >> 2;      // TMEM lane quadrant (hardware: warp % 4), column part 0..TC_PARTS-1
   const int row = quad * 32 + lane;                 // this thread's pair within the tile
   if (a.sel) {
     const long long t = a.sel[1];
@@ -136,8 +137,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_pair_rows_tc(TcArgs a, int ti
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(doneB + 1);
   float* m0s = reinterpret_cast<float*>(tmem_slot + 2);       // [Hp]
   float* pbs = m0s + Hp;                                      // [Hp]
-  float* xsum = reinterpret_cast<float*>(stg);                // [2][128] row-sum halves  (stage region: idle in epilogue B)
-  float* xgain = xsum + 2 * TC_M;                             // [2][128] gain halves
+  float* xsum = reinterpret_cast<float*>(stg);                // [TC_PARTS][128] row-sum parts  (stage region: idle in epilogue B)
+  float* xgain = xsum + TC_PARTS * TC_M;                      // [TC_PARTS][128] gain parts
   unsigned char* stgA = smem + 64 * 1024;
 
   if (tid == 0) {
@@ -164,7 +165,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_pair_rows_tc(TcArgs a, int ti
   for (int w = 0; w < 8; ++w) zw[w] = (w < W && row < cnt) ? a.zmask[(size_t)(pid0 + row) * W + w] : 0u;
 #pragma unroll
   for (int w = 0; w < 8; ++w) {
-    if (w < W && (w & 1) == half) {
+    if (w < W && (w % TC_PARTS) == half) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {   // 8 models -> one 16-byte core row
         const uint32_t b = zw[w] >> (8 * q);
@@ -243,7 +244,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_pair_rows_tc(TcArgs a, int ti
     unsigned char* dlo = opA + 64 * 1024;
     const uint32_t trow = tmem + ((uint32_t)(quad * 32) << 16);
 #pragma unroll 1
-    for (int cc = half * (TC_NODES / 64); cc < (half + 1) * (TC_NODES / 64); ++cc) {
+    for (int cc = half * (TC_NODES / 32 / TC_PARTS); cc < (half + 1) * (TC_NODES / 32 / TC_PARTS); ++cc) {
       float v[32];
       tmem_ld32(trow + cc * 32, v);
 #pragma unroll
@@ -308,7 +309,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_pair_rows_tc(TcArgs a, int ti
   {
     const uint32_t trow = tmem + ((uint32_t)(quad * 32) << 16);
     const int nch = Hp / 32;
-    const int ch_lo = half ? (nch + 1) / 2 : 0, ch_hi = half ? nch : (nch + 1) / 2;
+    const int per_part = (nch + TC_PARTS - 1) / TC_PARTS;
+    const int ch_lo = min(nch, half * per_part), ch_hi = min(nch, (half + 1) * per_part);
     float sum = 0.f;
 #pragma unroll
     for (int ch = 0; ch < 8; ++ch) {
@@ -323,7 +325,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_pair_rows_tc(TcArgs a, int ti
     }
     xsum[half * TC_M + row] = sum;
     __syncthreads();
-    sum = xsum[row] + xsum[TC_M + row];
+    sum = 0.f;
+#pragma unroll
+    for (int q = 0; q < TC_PARTS; ++q) sum += xsum[q * TC_M + row];
     uint32_t bad = 0;
     if (row < cnt && half == 0 && !isfinite(sum)) bad = CODA_B200_FLAG_NONFINITE_EIG;
     const float rden = 1.0f / fmaxf(sum, 1e-30f);                    // coda.py:114
@@ -360,7 +364,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_pair_rows_tc(TcArgs a, int ti
     if (want_gain) {
       xgain[half * TC_M + row] = g;
       __syncthreads();
-      if (half == 0 && row < cnt) a.gain[orow] = xgain[row] + xgain[TC_M + row];
+      if (half == 0 && row < cnt) {
+        float gs = 0.f;
+#pragma unroll
+        for (int q = 0; q < TC_PARTS; ++q) gs += xgain[q * TC_M + row];
+        a.gain[orow] = gs;
+      }
     }
     if (bad) atomicOr(a.flags, bad);
   }

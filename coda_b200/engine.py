@@ -587,9 +587,23 @@ class Engine:
         with self._on():
             self._loop_body()
 
+    def _try_capture(self, key, body):
+        """Capture `body` as graph `key`; a failed capture (driver / allocator state) falls back to eager launches."""
+        try:
+            g, n = self._capture(body)
+        except Exception as e:      # nothing was executed during the capture: the device state is still the pre-capture one
+            import warnings
+            warnings.warn(f"coda_b200: CUDA graph capture failed ({type(e).__name__}: {e}); continuing with eager launches")
+            self.use_graph = False
+            self.pending, self.scored, self.reported = False, False, False
+            torch.cuda.synchronize(self.dev)
+            return None, 0
+        self.graphs[key] = g
+        return g, n
+
     def loop_capture(self):
         with self._on():
-            self.graphs["loop"], self.launches_per_step = self._capture(self._loop_body)
+            _g, self.launches_per_step = self._try_capture("loop", self._loop_body)
 
     def loop_replay(self, k: int = 1):
         with self._on():
@@ -680,7 +694,7 @@ class Engine:
 
     def api_capture(self):
         with self._on():
-            self.graphs["api"], self.launches_per_api_step = self._capture(self._api_body)
+            _g, self.launches_per_api_step = self._try_capture("api", self._api_body)
 
     def label_run(self, eager_report: bool = True):
         with self._on():

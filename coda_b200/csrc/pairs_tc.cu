@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_pair_rows_tc(TcArgs a, int ti
         uint32_t hi[4], lo[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float d0 = expf(v[g * 8 + 2 * e]), d1 = expf(v[g * 8 + 2 * e + 1]);
+          const float d0 = __expf(v[g * 8 + 2 * e]), d1 = __expf(v[g * 8 + 2 * e + 1]);   // ex2.approx: 2 ulp, far inside the 16-bit limb pair D is cut into
           const __nv_bfloat16 h0 = __float2bfloat16_rn(d0), h1 = __float2bfloat16_rn(d1);
           hi[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
           lo[e] = pack_bf16(d0 - __bfloat162float(h0), d1 - __bfloat162float(h1));

@@ -15,7 +15,7 @@ from . import build as _build
 _LIB = None
 
 OK = 0
-VERSION = 200
+VERSION = 201
 MAX_WORLD = 16
 REC_WORDS = 8
 FLAG_NONFINITE_INPUT = 0x01
@@ -28,6 +28,7 @@ FLAG_NO_CANDIDATE = 0x40
 FLAG_XCHG_TIMEOUT = 0x80
 FLAG_NEGATIVE_PROB = 0x100
 FLAG_ROWSUM_WARN = 0x200
+FLAG_PIPELINE_TIMEOUT = 0x400
 FLAG_NAMES = {
     FLAG_NONFINITE_INPUT: "preds", FLAG_RANGE_INPUT: "preds range", FLAG_NONFINITE_TABLE: "pdf/cdf/integrand",
     FLAG_NONFINITE_PI: "pi_hat_xi", FLAG_NONFINITE_PBEST: "Pbest", FLAG_NONFINITE_EIG: "Pbest(beta) normalized",
@@ -81,6 +82,9 @@ SIGNATURES = {
     "coda_b200_pi_full_compact": (i32, [p, p, i64, p, i32, i64, i32, i32, p, p, p, p]),
     "coda_b200_pi_rank1_compact": (i32, [p, p, i64, p, i32, i64, i32, i32, p, f64, i32, p, p, p, p, p]),
     "coda_b200_pi_full": (i32, [p, i64, p, i32, i64, i32, p, p]),
+    "coda_b200_pi_full_tc_ok": (i32, [i32, i64, i32, i64]),
+    "coda_b200_pi_full_tc_scratch_bytes": (sz, [i32, i32]),
+    "coda_b200_pi_full_tc": (i32, [p, i64, p, i32, i64, i32, p, p, p, p]),
     "coda_b200_pi_reduce": (i32, [p, i64, i32, i32, p, p, p, p]),
     "coda_b200_shadow_build": (i32, [p, i64, i32, i64, i32, p, i32, i64, p, p]),
     "coda_b200_pi_rank1": (i32, [p, p, i32, i64, i32, p, f64, i32, p, p, p, p, i32, i32, p]),

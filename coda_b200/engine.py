@@ -124,6 +124,7 @@ class Engine:
         self.profile, self.profile_only = None, None
         self.xchg = None                                      # set by the group (dist.py) before the first exchange
         self._mailbox = None
+        self._pi_tc, self._pi_scratch = None, None           # tensor-core marginal pass: decided on first use
         self.stream = torch.cuda.Stream(device=self.dev) if own_stream else None
         self.side = torch.cuda.Stream(device=self.dev)
         self.ev_fork, self.ev_join, self.ev_tables = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
@@ -329,9 +330,25 @@ class Engine:
                        self.K, _ptr(dt), _ptr(rs), _ptr(self.U), s, n=3)
             del dt, rs
         else:
-            self._call("coda_b200_pi_full", _ptr(self.preds), self.model_stride, _ptr(self.D), H, N, C, _ptr(self.U), s)
+            self._pi_full()
         self._call("coda_b200_pi_reduce", _ptr(self.U), N, C, self.fx_shift, None, _ptr(self.pisum),
                    _ptr(self.flags), s)
+
+    def _pi_full(self):
+        """coda.py:227-229 over the dense slab: the tcgen05 kernel when the shape allows it (pi_tc.cu), else fp32 SIMT.
+        ``CODA_B200_PI_FULL=simt`` forces the SIMT kernel."""
+        H, N, C, s = self.H, self.N, self.C, self._s()
+        if self._pi_tc is None:
+            want = os.environ.get("CODA_B200_PI_FULL", "tc") != "simt"
+            self._pi_tc = bool(want and self.lib.coda_b200_pi_full_tc_ok(H, N, C, self.model_stride)
+                               and self.preds.data_ptr() % 16 == 0)
+            if self._pi_tc:
+                self._pi_scratch = self._e((int(self.lib.coda_b200_pi_full_tc_scratch_bytes(H, C)),), torch.uint8)
+        if self._pi_tc:
+            self._call("coda_b200_pi_full_tc", _ptr(self.preds), self.model_stride, _ptr(self.D), H, N, C, _ptr(self.U),
+                       _ptr(self._pi_scratch), _ptr(self.flags), s, n=2)
+        else:
+            self._call("coda_b200_pi_full", _ptr(self.preds), self.model_stride, _ptr(self.D), H, N, C, _ptr(self.U), s)
 
     def _build_rows(self):
         H, N, C, W, T, s = self.H, self.N, self.C, self.W, self.T, self._s()
@@ -505,7 +522,7 @@ class Engine:
         self.scored = False
         self.reported = False
         if self.mode == "recompute_all":
-            self._call("coda_b200_pi_full", _ptr(self.preds), self.model_stride, _ptr(self.D), H, N, C, _ptr(self.U), s)
+            self._pi_full()
             self._call("coda_b200_pi_reduce", _ptr(self.U), N, C, self.fx_shift, None, _ptr(self.pisum), _ptr(self.flags), s)
             self._tables(0, C)
             self._mixture()
@@ -758,6 +775,8 @@ class Engine:
             flags &= ~nat.FLAG_ROWSUM_WARN
             if not flags:
                 return
+        if flags & nat.FLAG_PIPELINE_TIMEOUT:
+            raise RuntimeError("coda_b200: the tensor-core marginal pass (k_pi_full_tc) stopped; its result is invalid")
         if flags & nat.FLAG_XCHG_TIMEOUT:
             raise RuntimeError("coda_b200: a shard did not arrive at an exchange within 2 s (peer crashed or not launched)")
         if flags & nat.FLAG_NO_CANDIDATE:

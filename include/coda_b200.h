@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define CODA_B200_VERSION 200
+#define CODA_B200_VERSION 201
 #define CODA_B200_NODES 256 /* quadrature nodes, coda/coda.py:79 */
 #define CODA_B200_MAX_WORLD 16
 #define CODA_B200_REC_WORDS 8 /* arg-max record: {bits vA, iA, cntA, bits vB, iB, bits v2A, bits v2B, 0} */
@@ -52,6 +52,7 @@ extern "C" {
 #define CODA_B200_FLAG_XCHG_TIMEOUT 0x80u    /* a peer never arrived at an exchange (2 s) */
 #define CODA_B200_FLAG_NEGATIVE_PROB 0x100u  /* util._check_prob: probability < -1e-12 (util.py:33-35) */
 #define CODA_B200_FLAG_ROWSUM_WARN 0x200u    /* util._check_prob: |row sum - 1| > 1e-4 (util.py:37-39), a warning */
+#define CODA_B200_FLAG_PIPELINE_TIMEOUT 0x400u /* a TMA / tensor-core pipeline stopped (pi_full_tc); the result is invalid */
 
 typedef void* coda_stream_t;
 
@@ -115,6 +116,15 @@ int coda_b200_init_dirichlets(const int64_t* conf_fx, const int64_t* conf_rest, 
 /* U[n][c] = sum_h sum_s D[h][c][s] preds[h][n][s]  (coda.py:227-229, `adjusted` never stored). */
 int coda_b200_pi_full(const float* preds, int64_t model_stride, const float* D, int H, int64_t N, int C, float* U,
                       coda_stream_t stream);
+
+/* The same contraction on the tensor cores (tcgen05, TMEM accumulators, bulk-TMA slab stream): both operands are cut
+ * into two bf16 limbs, 4 MMAs per K = 16 chunk, accumulators drained to fp32 registers every 4 models (pi_tc.cu).
+ * Usable when pi_full_tc_ok(...) != 0 (16 <= C <= 128, C % 4 == 0, model_stride % 4 == 0); `scratch` =
+ * pi_full_tc_scratch_bytes(H, C) bytes (the D limbs).  A stopped pipeline sets CODA_B200_FLAG_PIPELINE_TIMEOUT. */
+int coda_b200_pi_full_tc_ok(int H, int64_t N, int C, int64_t model_stride);
+size_t coda_b200_pi_full_tc_scratch_bytes(int H, int C);
+int coda_b200_pi_full_tc(const float* preds, int64_t model_stride, const float* D, int H, int64_t N, int C, float* U,
+                         void* scratch, uint32_t* flags, coda_stream_t stream);
 
 /* Row-normalise with the 1e-12 clamp (coda.py:230) and accumulate sum_n pi_hat_xi[n][:]
  * (coda.py:232) into pisum_fx [C] (int64 fixed point, ACCUMULATED).  xi_out may be NULL. */

@@ -653,3 +653,53 @@ def test_marginal_refresh_variants_carry_identical_bits(shape, monkeypatch):
         monkeypatch.delenv("CODA_B200_R1")
         picks = {v: s.get_next_item_to_label() for v, s in sels.items()}
         assert picks["v4"] == picks["tma"] == picks["v1"]
+
+
+@pytest.mark.parametrize("shape", [(256, 1000, 100, 1.0), (5, 128, 16, 1.0), (9, 700, 128, 1.0), (30, 257, 20, 3e5),
+                                   (64, 4100, 52, 1e-3), (3, 40, 24, 1.0)])
+def test_tensor_core_marginals_match_fp64(shape):
+    """coda.py:227-229 on tcgen05 (k_pi_full_tc: two fp16 limbs per operand, TMEM accumulators drained every 4 models)
+    against an fp64 contraction and against the fp32 SIMT kernel, through the raw C ABI: ragged last tile, class counts
+    that are not a multiple of 16, a model count that is not a multiple of the drain group, Dirichlet parameters far
+    outside the fp16 range (rescaled by a power of two inside), a slab VIEW (model stride larger than the shard), and
+    bit-identical rows wherever the tile boundaries fall (the shard-count invariance)."""
+    from coda_b200 import _native as nat
+    lib = nat.load()
+    H, N, C, dscale = shape
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(H * 1000 + C)
+    preds = torch.softmax(3 * torch.randn((H, N + 40, C), generator=g), dim=-1).to(dev)
+    D = (0.2 + 2 * torch.rand((H, C, C), generator=g)).to(dev)
+    D += 5 * torch.eye(C, device=dev)
+    D *= dscale
+    st = torch.cuda.current_stream().cuda_stream
+    ld = (N + 40) * C
+    assert lib.coda_b200_pi_full_tc_ok(H, N, C, ld)
+    scratch = torch.empty(int(lib.coda_b200_pi_full_tc_scratch_bytes(H, C)), dtype=torch.uint8, device=dev)
+    flags = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    def tc(first, n):
+        U = torch.full((n, C), float("nan"), device=dev)
+        view = preds[:, first:]
+        nat.check(lib.coda_b200_pi_full_tc(view.data_ptr(), ld, D.data_ptr(), H, n, C, U.data_ptr(), scratch.data_ptr(),
+                                           flags.data_ptr(), st), "pi_full_tc")
+        torch.cuda.synchronize()
+        return U
+    U = tc(0, N)
+    assert int(flags.item()) == 0
+    ref = torch.einsum("hns,hcs->nc", preds[:, :N].double(), D.double())
+    rel = ((U.double() - ref).abs() / ref).max().item()
+    assert rel < 5e-6, rel                                     # the fp32 inputs are carried exactly; what is left is the
+    xi, xr = U.double() / U.double().sum(1, keepdim=True), ref / ref.sum(1, keepdim=True)   # truncating accumulate of 4 models
+    assert ((xi - xr).abs() / xr).max().item() < 2e-6          # (a common factor: it cancels in the row normalisation)
+    simt = torch.empty((N, C), device=dev)
+    nat.check(lib.coda_b200_pi_full(preds.data_ptr(), ld, D.data_ptr(), H, N, C, simt.data_ptr(), st), "pi_full")
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(U.cpu().numpy(), simt.cpu().numpy(), rtol=1e-4)       # the fp32 FMA chain is the looser one
+    if H * C >= 20000:                                                                 # (H*C sequential roundings per entry)
+        xs = simt.double() / simt.double().sum(1, keepdim=True)
+        assert ((xi - xr).abs() / xr).max().item() < ((xs - xr).abs() / xr).max().item()
+    # a shard that starts 40 items (not a tile multiple) later computes the same bits for the items both hold
+    if N > 40 and (40 * C) % 4 == 0:
+        V = tc(40, N)
+        assert torch.equal(V[: N - 40], U[40:])

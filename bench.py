@@ -519,6 +519,33 @@ def main():
                 tc=bool(eng.use_tc), mode=eng.mode)
     kernels = kernel_table(prof)
 
+    def marginals_full(eng):
+        """The construction / recompute_all pass (coda.py:227-229) on this shard: the tcgen05 kernel beside the fp32 SIMT
+        kernel, CUDA events around one launch each (U is rewritten with the same values the steps maintained)."""
+        if eng.compact is not None or not eng._pi_tc:
+            return None
+        out = {}
+        for name, use_tc in (("k_pi_full_tc", True), ("k_pi_full", False)):
+            eng._pi_tc = use_tc
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            with eng._on():
+                st = eng._cur()
+                a.record(st)
+                eng._pi_full()
+                b.record(st)
+            torch.cuda.synchronize()
+            t = a.elapsed_time(b)
+            out[name] = {"ms": t, "slab_GB_per_s": 4.0 * eng.H * eng.N * eng.C / (t * 1e-3) / 1e9,
+                         "fp32_equiv_TFLOP_per_s": 2.0 * eng.H * eng.N * eng.C * eng.C / (t * 1e-3) / 1e12}
+        eng._pi_tc = True
+        with eng._on():
+            eng._pi_full()                                       # leave the tensor-core result in U, as construction did
+        torch.cuda.synchronize()
+        eng.check_flags(sync=True)
+        return out
+    marg = marginals_full(eng) if world == 1 else None
+
     extra = {}
     extra_list = [x for x in args.extra_modes.split(",") if x and x != args.mode]
     import gc
@@ -577,6 +604,7 @@ def main():
             "roofline": roof,
             "kernel_ms": kernels,
             "exchange_wait": exchange,
+            "marginals_full": marg,
             "modes": extra,
             "cpu_baseline": cpu,
             "first_picks": {"device_loop": picks_dev[:8], "api": [p[0] for p in picks_api[:8]]},

@@ -107,12 +107,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "{\n\t"
       ".reg .pred p;\n\t"
       "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"   // suspend-time hint: the hardware parks the warp
+      "@p bra DONE;\n\t"                                                   // instead of spinning on the issue slots
       "bra WAIT_LOOP;\n\t"
       "DONE:\n\t"
       "}" ::"r"(smem_u32(bar)),
-      "r"(parity)
+      "r"(parity), "r"(20000u)
       : "memory");
 }
 // global -> shared bulk copy; bytes % 16 == 0, both addresses 16-byte aligned.

@@ -160,22 +160,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_pair_rows_tc(TcArgs a, int ti
     pbs[h] = a.PB[(size_t)c * Hp + h];
   }
   // ---- Z operand: row = this thread's pair, K = models, bf16 {0, 1} ----------------------------
-  uint32_t zw[8];
+#pragma unroll 1
+  for (int w = half; w < W; w += TC_PARTS) {       // rolled: one copy of the body instead of eight (instruction cache)
+    const uint32_t z = row < cnt ? a.zmask[(size_t)(pid0 + row) * W + w] : 0u;
 #pragma unroll
-  for (int w = 0; w < 8; ++w) zw[w] = (w < W && row < cnt) ? a.zmask[(size_t)(pid0 + row) * W + w] : 0u;
-#pragma unroll
-  for (int w = 0; w < 8; ++w) {
-    if (w < W && (w % TC_PARTS) == half) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {   // 8 models -> one 16-byte core row
-        const uint32_t b = zw[w] >> (8 * q);
-        uint4 v;
-        v.x = ((b & 1u) ? 0x3F80u : 0u) | ((b & 2u) ? 0x3F800000u : 0u);
-        v.y = ((b & 4u) ? 0x3F80u : 0u) | ((b & 8u) ? 0x3F800000u : 0u);
-        v.z = ((b & 16u) ? 0x3F80u : 0u) | ((b & 32u) ? 0x3F800000u : 0u);
-        v.w = ((b & 64u) ? 0x3F80u : 0u) | ((b & 128u) ? 0x3F800000u : 0u);
-        *reinterpret_cast<uint4*>(opA + core_off(row, w * 32 + q * 8, TC_M)) = v;
-      }
+    for (int q = 0; q < 4; ++q) {   // 8 models -> one 16-byte core row
+      const uint32_t b = z >> (8 * q);
+      uint4 v;
+      v.x = ((b & 1u) ? 0x3F80u : 0u) | ((b & 2u) ? 0x3F800000u : 0u);
+      v.y = ((b & 4u) ? 0x3F80u : 0u) | ((b & 8u) ? 0x3F800000u : 0u);
+      v.z = ((b & 16u) ? 0x3F80u : 0u) | ((b & 32u) ? 0x3F800000u : 0u);
+      v.w = ((b & 64u) ? 0x3F80u : 0u) | ((b & 128u) ? 0x3F800000u : 0u);
+      *reinterpret_cast<uint4*>(opA + core_off(row, w * 32 + q * 8, TC_M)) = v;
     }
   }
   fence_proxy_async();
@@ -311,17 +307,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_pair_rows_tc(TcArgs a, int ti
     const int nch = Hp / 32;
     const int per_part = (nch + TC_PARTS - 1) / TC_PARTS;
     const int ch_lo = min(nch, half * per_part), ch_hi = min(nch, (half + 1) * per_part);
+    // The chunk loops stay ROLLED: unrolled eight ways (one copy per possible chunk, each warp running two of them) the
+    // epilogue was 10 000 SASS lines = 160 KB, and ncu attributed 43 % of the kernel to it with instruction-fetch stalls
+    // (stall_no_inst) on top.  The mask words of this thread's (at most two) chunks are re-read (L1 hits).
+    uint32_t zsel[2] = {0u, 0u};
+    if (row < cnt) {
+      if (ch_lo < ch_hi) zsel[0] = a.zmask[(size_t)(pid0 + row) * W + ch_lo];
+      if (ch_lo + 1 < ch_hi) zsel[1] = a.zmask[(size_t)(pid0 + row) * W + ch_lo + 1];
+    }
     float sum = 0.f;
+#pragma unroll 1
+    for (int ch = ch_lo; ch < ch_hi; ++ch) {
+      float p0[32], p1[32];
+      tmem_ld32(trow + ch * 32, p0);
+      tmem_ld32(trow + 256 + ch * 32, p1);
+      const uint32_t zb = (ch == ch_lo) ? zsel[0] : zsel[1];
 #pragma unroll
-    for (int ch = 0; ch < 8; ++ch) {
-      if (ch >= ch_lo && ch < ch_hi) {
-        float p0[32], p1[32];
-        tmem_ld32(trow + ch * 32, p0);
-        tmem_ld32(trow + 256 + ch * 32, p1);
-        const uint32_t zb = zw[ch];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) sum += ((zb >> i) & 1u) ? p1[i] : p0[i];
-      }
+      for (int i = 0; i < 32; ++i) sum += ((zb >> i) & 1u) ? p1[i] : p0[i];
     }
     xsum[half * TC_M + row] = sum;
     __syncthreads();
@@ -336,13 +338,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_pair_rows_tc(TcArgs a, int ti
     const int orow = row < cnt ? a.row_of[pid0 + row] : 0;
     if (row < cnt && half == 0 && sum < 0.9999e-30f) bad |= CODA_B200_FLAG_ROWSUM_WARN;    // util.py:37-39
     float* cache = (a.ph_cache && row < cnt) ? a.ph_cache + (size_t)orow * Hp : nullptr;
-#pragma unroll
-    for (int ch = 0; ch < 8; ++ch) {
-      if (ch < ch_lo || ch >= ch_hi) continue;
+#pragma unroll 1
+    for (int ch = ch_lo; ch < ch_hi; ++ch) {
       float p0[32], p1[32];
       tmem_ld32(trow + ch * 32, p0);
       tmem_ld32(trow + 256 + ch * 32, p1);
-      const uint32_t zb = zw[ch];
+      const uint32_t zb = (ch == ch_lo) ? zsel[0] : zsel[1];
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         const int h = ch * 32 + i;

@@ -40,6 +40,7 @@ WORKLOADS = {
     # the reference cannot run it (coda.py:227 materialises a second slab)
     "cfg5": dict(H=1024, N=4_000_000, C=1000, K=4, compact=True),
     "cfg5mini": dict(H=1024, N=131_072, C=1000, K=4, compact=True),
+    "cfg5shard": dict(H=1024, N=500_000, C=1000, K=4, compact=True),     # what one of the 8 GPUs of cfg5 holds
 }
 METRIC = "acquisition steps/sec (M=256,N=1e6,C=100)"
 
@@ -278,7 +279,7 @@ def run_reference(args):
 
 # ---------------------------------------------------------------------------------------------------
 HOT = {   # C-ABI entry point -> kernel name printed in the roofline line
-    "coda_b200_row_gains": "k_row_gains", "coda_b200_gain_eig": "k_eig_assemble_g8", "coda_b200_pi_rank1_compact": "k_pi_rank1_compact", "coda_b200_pi_rank1": "k_pi_rank1", "coda_b200_pair_rows_tc": "k_pair_rows_tc",
+    "coda_b200_row_gains": "k_row_gains", "coda_b200_gain_eig": "k_eig_assemble_g8", "coda_b200_pi_rank1_compact": "k_pi_rank1_compact", "coda_b200_pi_rank1_index": "k_r1i_scatter+k_r1i_rows", "coda_b200_pi_rank1": "k_pi_rank1", "coda_b200_pair_rows_tc": "k_pair_rows_tc",
     "coda_b200_pair_rows": "k_pair_rows", "coda_b200_pi_full": "k_pi_full", "coda_b200_template_gains": "k_template_gains",
     "coda_b200_beta_tables": "k_beta_nodes+k_beta_combine+k_pb_normalize", "coda_b200_step_select": "k_step_select",
     "coda_b200_step_mixture": "k_step_mixture",
@@ -308,6 +309,8 @@ def algorithmic_bytes(eng):
         # one 24-byte entry per gathered model and item (the models that disagree with the majority on the labeled item;
         # read from the gather list of the last step) + the U row pass + the ensemble column
         "coda_b200_pi_rank1_compact": 6 * getattr(eng, "K", 4) * gathered_models(eng) * N + 4 * N * C + 8 * N,
+        # inverted index: H lists of ~N K / C entries (8 B) + rest sums + the int64 scatter target (read, cleared) + the U row pass
+        "coda_b200_pi_rank1_index": 8 * H * N * getattr(eng, "K", 4) // max(1, C) + 4 * N + 16 * N + 4 * N * C + 4 * N,
         # one float per (model, item) + the U row pass (read all, write one column) + the ensemble column
         "coda_b200_pi_rank1": 4 * H * N + 4 * N * C + 4 * N + 4 * N,
         "coda_b200_pi_full": 4 * H * N * C + 4 * N * C,

@@ -15,7 +15,7 @@ from . import build as _build
 _LIB = None
 
 OK = 0
-VERSION = 201
+VERSION = 202
 MAX_WORLD = 16
 REC_WORDS = 8
 FLAG_NONFINITE_INPUT = 0x01
@@ -81,6 +81,9 @@ SIGNATURES = {
     "coda_b200_confusion_compact": (i32, [p, p, i64, p, i32, i64, i32, i32, i32, p, p, p]),
     "coda_b200_pi_full_compact": (i32, [p, p, i64, p, i32, i64, i32, i32, p, p, p, p]),
     "coda_b200_pi_rank1_compact": (i32, [p, p, i64, p, i32, i64, i32, i32, p, f64, i32, p, p, p, p, p]),
+    "coda_b200_compact_index_count": (i32, [p, i64, i32, i64, i32, i32, p, p]),
+    "coda_b200_compact_index_fill": (i32, [p, p, i64, i32, i64, i32, i32, p, p, p, p]),
+    "coda_b200_pi_rank1_index": (i32, [p, p, p, p, i32, i64, i32, p, f64, i32, p, p, p, p, p, p]),
     "coda_b200_pi_full": (i32, [p, i64, p, i32, i64, i32, p, p]),
     "coda_b200_pi_full_tc_ok": (i32, [i32, i64, i32, i64]),
     "coda_b200_pi_full_tc_scratch_bytes": (sz, [i32, i32]),

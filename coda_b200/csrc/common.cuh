@@ -77,6 +77,17 @@ __device__ __forceinline__ float ent_term(float m) {
   return -q * __log2f(q);
 }
 
+// ---- row normalisation, coda.py:230-231: xi = u / den for every entry of a row ----------------------------
+// One IEEE division per row (rden = 1 / den), then per entry the Markstein correction  q = u rden,  q += (u - den q) rden,
+// which returns the correctly rounded quotient (the same bits as u / den, except for the measure-zero case of a den
+// whose significand is all ones) in 3 instructions instead of the ~20 of the division subroutine: at C = 1000 the
+// row pass was instruction-bound on it.  EVERY kernel that normalises rows of U goes through this function, so the
+// column sums of the full pass, of every rank-1 variant and of a resumed run stay bit-identical to each other.
+__device__ __forceinline__ float row_quot(float u, float den, float rden) {
+  const float q = u * rden;
+  return fmaf(fmaf(-den, q, u), rden, q);
+}
+
 // ---- fixed-point accumulation (order- and shard-count-independent sums) ---------------
 // Values in [0, 1] are scaled by 2^shift and summed as int64; the host picks shift so that
 // N_global * 2^shift < 2^62.

@@ -358,8 +358,9 @@ __global__ void __launch_bounds__(256) k_pi_rank1_compact(const uint16_t* __rest
         s = warp_sum(s);
         if (!isfinite(s)) bad |= CODA_B200_FLAG_NONFINITE_PI;
         const float den = fmaxf(s, 1e-12f);                             // coda.py:230 clamp_(min=1e-12)
+        const float rden = 1.0f / den;
 #pragma unroll
-        for (int k = 0; k < KR; ++k) racc[k] += to_fx(u[k] / den, fxs);
+        for (int k = 0; k < KR; ++k) racc[k] += to_fx(row_quot(u[k], den, rden), fxs);
         continue;
       }
       float s = 0.f;
@@ -374,7 +375,8 @@ __global__ void __launch_bounds__(256) k_pi_rank1_compact(const uint16_t* __rest
       s = warp_sum(s);
       if (!isfinite(s)) bad |= CODA_B200_FLAG_NONFINITE_PI;
       const float den = fmaxf(s, 1e-12f);                               // coda.py:230 clamp_(min=1e-12)
-      for (int c = lane; c < C; c += 32) wacc[c] += to_fx(urow[c] / den, fxs);   // column t was rewritten by this lane
+      const float rden = 1.0f / den;
+      for (int c = lane; c < C; c += 32) wacc[c] += to_fx(row_quot(urow[c], den, rden), fxs);   // column t was rewritten by this lane
     }
   }
   if (KCU > 0) {
@@ -417,5 +419,263 @@ extern "C" int coda_b200_pi_rank1_compact(const uint16_t* ids, const float* prob
   else LAUNCH_R1C(0);
 #undef LAUNCH_R1C
   CODA_LAUNCH_OK("k_pi_rank1_compact");
+  return CODA_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// Inverted index of the compact slab: for every (model h, class c) the items whose top-K list holds c, as
+// {item, probs - rest} pairs.  The rank-1 refresh needs sum_h preds[h][n][j_h] for ONE class j_h per model:
+//
+//     sum_h preds[h][n][j_h] = R[n] + sum_{h : j_h in topK(h, n)} (p_{h,n,j_h} - rest(h, n)),    R[n] = sum_h rest(h, n)
+//
+// so instead of scanning the whole slab every step (24 bytes per (h, n): 12 GB per shard at configs[4]) a step reads
+// the H lists (h, j_h) -- N K / C entries each on average, 16 MB in all -- and scatters them into a per-item int64
+// fixed-point accumulator (order-independent, so the result does not depend on how the lists were filled or on the
+// shard count), then makes the one pass over U it has to make anyway.  Built once: count -> prefix sums (host
+// plumbing) -> fill.  Same bytes as the slab itself (8 per entry).
+// ---------------------------------------------------------------------------------------
+#define CIDX_ITEMS 4096      // items per CTA and model in the count / fill passes
+
+// counts[h][c] += #{(n, k) : ids[h][n][k] == c}, n in this CTA's chunk (shared-memory histogram first)
+__global__ void __launch_bounds__(256) k_cidx_count(const uint16_t* __restrict__ ids, long long model_stride_e, long long N,
+                                                    int C, int K, unsigned long long* __restrict__ counts) {
+  extern __shared__ int s_hist[];
+  const int h = blockIdx.y;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) s_hist[c] = 0;
+  __syncthreads();
+  const long long n0 = (long long)blockIdx.x * CIDX_ITEMS, n1 = min(N, n0 + CIDX_ITEMS);
+  const uint16_t* base = ids + (size_t)h * model_stride_e;
+  for (long long e = n0 * K + threadIdx.x; e < n1 * K; e += blockDim.x) {
+    const int c = base[e];
+    if (c < C) atomicAdd(&s_hist[c], 1);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x)
+    if (s_hist[c]) atomicAdd(counts + (size_t)h * C + c, (unsigned long long)s_hist[c]);
+}
+
+// second pass: every CTA reserves one contiguous range per class it meets (one global atomic each), then places its
+// entries inside those ranges with shared-memory cursors.  ent[pos] = {item, float bits of (p - rest)}.
+template <int K>
+__global__ void __launch_bounds__(256) k_cidx_fill(const uint16_t* __restrict__ ids, const float* __restrict__ probs,
+                                                   long long model_stride_e, long long N, int C,
+                                                   unsigned long long* __restrict__ cursor, uint2* __restrict__ ent) {
+  extern __shared__ int s_mem[];
+  int* s_cnt = s_mem;                                                       // [C] entries of this chunk per class
+  int* s_cur = s_mem + C;                                                   // [C] placed so far
+  unsigned long long* s_base = reinterpret_cast<unsigned long long*>(s_mem + 2 * C + ((2 * C) & 1));   // [C] reserved range start
+  const int h = blockIdx.y;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) { s_cnt[c] = 0; s_cur[c] = 0; }
+  __syncthreads();
+  const long long n0 = (long long)blockIdx.x * CIDX_ITEMS, n1 = min(N, n0 + CIDX_ITEMS);
+  const uint16_t* ibase = ids + (size_t)h * model_stride_e;
+  for (long long e = n0 * K + threadIdx.x; e < n1 * K; e += blockDim.x) {
+    const int c = ibase[e];
+    if (c < C) atomicAdd(&s_cnt[c], 1);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x)
+    if (s_cnt[c]) s_base[c] = atomicAdd(cursor + (size_t)h * C + c, (unsigned long long)s_cnt[c]);
+  __syncthreads();
+  const float inv_cmk = 1.0f / (float)(C - K);
+  for (long long n = n0 + threadIdx.x; n < n1; n += blockDim.x) {
+    float p[K];
+    int id[K];
+    compact_load<K>(ids, probs, (size_t)h * model_stride_e + (size_t)n * K, p, id);
+    const float r = compact_rest<K>(p, inv_cmk);
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      if (id[j] < C) {
+        const unsigned long long pos = s_base[id[j]] + (unsigned long long)atomicAdd(&s_cur[id[j]], 1);
+        ent[pos] = make_uint2((unsigned)n, __float_as_uint(p[j] - r));
+      }
+    }
+  }
+}
+
+// R[n] = sum_h rest(h, n), models in order (one thread per item)
+template <int K>
+__global__ void __launch_bounds__(256) k_cidx_rest(const uint16_t* __restrict__ ids, const float* __restrict__ probs,
+                                                   long long model_stride_e, int H, long long N, int C,
+                                                   float* __restrict__ R) {
+  const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const float inv_cmk = 1.0f / (float)(C - K);
+  float s = 0.f;
+  for (int h = 0; h < H; ++h) {
+    float p[K];
+    int id[K];
+    compact_load<K>(ids, probs, (size_t)h * model_stride_e + (size_t)n * K, p, id);
+    s += compact_rest<K>(p, inv_cmk);
+  }
+  R[n] = s;
+}
+
+extern "C" int coda_b200_compact_index_count(const uint16_t* ids, int64_t model_stride, int H, int64_t N, int C, int K,
+                                             int64_t* counts, coda_stream_t stream) {
+  CODA_CHECK_ARG(ids && counts, "compact_index_count: null pointer");
+  CODA_CHECK_ARG(H >= 1 && N >= 1 && N < (1LL << 32) && K >= 1 && K <= CK_MAX && (size_t)C * 4 <= 160 * 1024,
+                 "compact_index_count: bad dims");
+  const dim3 grid((unsigned)((N + CIDX_ITEMS - 1) / CIDX_ITEMS), (unsigned)H);
+  const size_t smem = (size_t)C * 4;
+  CODA_CUDA_OK(cudaFuncSetAttribute(k_cidx_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_cidx_count<<<grid, 256, smem, as_stream(stream)>>>(ids, (long long)model_stride, N, C, K,
+                                                       reinterpret_cast<unsigned long long*>(counts));
+  CODA_LAUNCH_OK("k_cidx_count");
+  return CODA_B200_OK;
+}
+
+extern "C" int coda_b200_compact_index_fill(const uint16_t* ids, const float* probs, int64_t model_stride, int H, int64_t N,
+                                            int C, int K, int64_t* cursor, void* entries, float* rest_sum,
+                                            coda_stream_t stream) {
+  CODA_CHECK_ARG(ids && probs && cursor && entries && rest_sum, "compact_index_fill: null pointer");
+  CODA_CHECK_ARG(H >= 1 && N >= 1 && N < (1LL << 32) && K >= 1 && K <= CK_MAX && K < C && (size_t)C * 16 + 8 <= 160 * 1024,
+                 "compact_index_fill: bad dims");
+  const dim3 grid((unsigned)((N + CIDX_ITEMS - 1) / CIDX_ITEMS), (unsigned)H);
+  const size_t smem = (size_t)C * 16 + 8;
+  CK_DISPATCH(K, {
+    CODA_CUDA_OK(cudaFuncSetAttribute(k_cidx_fill<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_cidx_fill<KK><<<grid, 256, smem, as_stream(stream)>>>(ids, probs, (long long)model_stride, N, C,
+                                                            reinterpret_cast<unsigned long long*>(cursor),
+                                                            reinterpret_cast<uint2*>(entries));
+    k_cidx_rest<KK><<<(unsigned)((N + 255) / 256), 256, 0, as_stream(stream)>>>(ids, probs, (long long)model_stride, H, N, C,
+                                                                                 rest_sum);
+  });
+  CODA_LAUNCH_OK("k_cidx_fill");
+  return CODA_B200_OK;
+}
+
+// ---- the rank-1 refresh from the index ------------------------------------------------------------------------
+// scatter: CTA (x, h) walks its share of list (h, jvec[h]); delta_fx[n] += (p - rest) in int64 fixed point
+__global__ void __launch_bounds__(256) k_r1i_scatter(const long long* __restrict__ off, const uint2* __restrict__ ent,
+                                                     const int32_t* __restrict__ jvec, const int32_t* __restrict__ hdr,
+                                                     int C, float fxs, unsigned long long* __restrict__ delta) {
+  if (hdr[0] == 0 && hdr[1] < 0) return;                      // no label was applied in this step (see apply_label)
+  const int h = blockIdx.y;
+  const int j = jvec[h];
+  const long long lo = off[(size_t)h * C + j], hi = off[(size_t)h * C + j + 1];
+  for (long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (long long)gridDim.x * blockDim.x) {
+    const uint2 e = __ldg(ent + i);
+    atomicAdd(delta + e.x, (unsigned long long)to_fx(__uint_as_float(e.y), fxs));
+  }
+}
+
+// rows: d = R[n] + delta[n] (then cleared), U[n][t] += lr d, normalise, column sums -- the row walk of k_pi_rank1_compact
+template <int KCU>
+__global__ void __launch_bounds__(256) k_r1i_rows(const float* __restrict__ R, unsigned long long* __restrict__ delta,
+                                                  long long N, int C, const long long* __restrict__ sel,
+                                                  const int32_t* __restrict__ hdr, float lr, float inv_fxd, float fxs,
+                                                  float* __restrict__ U, unsigned long long* __restrict__ pisum_fx,
+                                                  uint32_t* __restrict__ flags) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  long long* wacc_all = reinterpret_cast<long long*>(smem_raw);                 // [8][C]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = (int)sel[1];
+  const bool valid = !(hdr[0] == 0 && hdr[1] < 0);
+  long long* wacc = wacc_all + (size_t)warp * C;
+  for (int c = lane; c < C; c += 32) wacc[c] = 0;
+  __syncthreads();
+  uint32_t bad = 0;
+  long long racc[KCU > 0 ? KCU : 1];
+#pragma unroll
+  for (int k = 0; k < (KCU > 0 ? KCU : 1); ++k) racc[k] = 0;
+  for (long long n0 = (long long)blockIdx.x * 256 + warp * 32; n0 < N; n0 += (long long)gridDim.x * 256) {
+    const long long n = n0 + lane;
+    float d = 0.f;
+    if (n < N && valid) {
+      const long long dv = (long long)delta[n];
+      if (dv) delta[n] = 0ull;
+      d = R[n] + (float)dv * inv_fxd;
+    }
+    const float dl = lr * d;
+    const int rows = (int)min(32LL, N - n0);
+    for (int r2 = 0; r2 < rows; ++r2) {
+      const float dr = __shfl_sync(CODA_FULL, dl, r2);
+      float* urow = U + (size_t)(n0 + r2) * C;
+      if (KCU > 0) {
+        constexpr int KR = KCU > 0 ? KCU : 1;
+        float u[KR];
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < KR; ++k) {
+          const int c = lane + 32 * k;
+          u[k] = c < C ? urow[c] : 0.f;
+          if (c == t) {
+            u[k] += dr;
+            urow[c] = u[k];
+          }
+          s += u[k];
+        }
+        s = warp_sum(s);
+        if (!isfinite(s)) bad |= CODA_B200_FLAG_NONFINITE_PI;
+        const float den = fmaxf(s, 1e-12f);                             // coda.py:230 clamp_(min=1e-12)
+        const float rden = 1.0f / den;
+#pragma unroll
+        for (int k = 0; k < KR; ++k) racc[k] += to_fx(row_quot(u[k], den, rden), fxs);
+        continue;
+      }
+      float s = 0.f;
+      for (int c = lane; c < C; c += 32) {
+        float u = urow[c];
+        if (c == t) {
+          u += dr;
+          urow[c] = u;
+        }
+        s += u;
+      }
+      s = warp_sum(s);
+      if (!isfinite(s)) bad |= CODA_B200_FLAG_NONFINITE_PI;
+      const float den = fmaxf(s, 1e-12f);                               // coda.py:230 clamp_(min=1e-12)
+      const float rden = 1.0f / den;
+      for (int c = lane; c < C; c += 32) wacc[c] += to_fx(row_quot(urow[c], den, rden), fxs);   // column t was rewritten by this lane
+    }
+  }
+  if (KCU > 0) {
+#pragma unroll
+    for (int k = 0; k < (KCU > 0 ? KCU : 1); ++k) {
+      const int c = lane + 32 * k;
+      if (c < C) wacc[c] = racc[k];
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    long long s2 = 0;
+    for (int w = 0; w < 8; ++w) s2 += wacc_all[(size_t)w * C + c];
+    if (s2) atomicAdd(pisum_fx + c, (unsigned long long)s2);
+  }
+  if (bad) atomicOr(flags, bad);
+}
+
+#define CIDX_FX_SHIFT 40     // |sum_h (p - rest)| <= H <= 2^11: 2^51 at most
+
+extern "C" int coda_b200_pi_rank1_index(const int64_t* offsets, const void* entries, const float* rest_sum,
+                                        const int32_t* jvec, int H, int64_t N, int C, const int64_t* sel, double lr,
+                                        int fx_shift, const int32_t* terms, int64_t* delta, float* U, int64_t* pisum_fx,
+                                        uint32_t* flags, coda_stream_t stream) {
+  CODA_CHECK_ARG(offsets && entries && rest_sum && jvec && sel && terms && delta && U && pisum_fx && flags,
+                 "pi_rank1_index: null pointer");
+  CODA_CHECK_ARG(H >= 1 && H <= 2048 && N >= 1 && C >= 2, "pi_rank1_index: bad dims");
+  const size_t smem = (size_t)8 * C * 8;
+  CODA_CHECK_ARG(smem <= 200 * 1024, "pi_rank1_index: C=%d too large", C);
+  k_r1i_scatter<<<dim3(8, (unsigned)H), 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const long long*>(offsets), reinterpret_cast<const uint2*>(entries), jvec, terms, C,
+      exp2f((float)CIDX_FX_SHIFT), reinterpret_cast<unsigned long long*>(delta));
+  CODA_LAUNCH_OK("k_r1i_scatter");
+  int grid = (int)min((long long)(N + 255) / 256, (long long)coda_sm_count() * 8);
+  if (grid < 1) grid = 1;
+#define LAUNCH_R1I(KCU)                                                                                              \
+  do {                                                                                                               \
+    CODA_CUDA_OK(cudaFuncSetAttribute(k_r1i_rows<KCU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+    k_r1i_rows<KCU><<<grid, 256, smem, as_stream(stream)>>>(                                                         \
+        rest_sum, reinterpret_cast<unsigned long long*>(delta), N, C, reinterpret_cast<const long long*>(sel), terms, \
+        (float)lr, exp2f(-(float)CIDX_FX_SHIFT), exp2f((float)fx_shift), U,                                          \
+        reinterpret_cast<unsigned long long*>(pisum_fx), flags);                                                     \
+  } while (0)
+  if (C <= 128) LAUNCH_R1I(4);
+  else if (C <= 512) LAUNCH_R1I(16);
+  else if (C <= 1024) LAUNCH_R1I(32);
+  else LAUNCH_R1I(0);
+#undef LAUNCH_R1I
+  CODA_LAUNCH_OK("k_r1i_rows");
   return CODA_B200_OK;
 }

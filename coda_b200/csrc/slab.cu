@@ -514,8 +514,9 @@ __device__ __forceinline__ void row_accumulate(float* __restrict__ urow, int C, 
   s = warp_sum(s);
   if (!isfinite(s)) bad |= CODA_B200_FLAG_NONFINITE_PI;
   const float den = fmaxf(s, 1e-12f);                               // coda.py:230 clamp_(min=1e-12)
+  const float rden = 1.0f / den;
   for (int c = lane; c < C; c += 32) {
-    float xi = urow[c] / den;   // column t was rewritten above by this same lane
+    float xi = row_quot(urow[c], den, rden);   // column t was rewritten above by this same lane
 
     if (xi_out) xi_out[c] = xi;
     wacc[c] += to_fx(xi, fxs);
@@ -640,8 +641,9 @@ __device__ __forceinline__ void rows_accumulate_reg(float* __restrict__ U, long 
     s = warp_sum(s);
     if (!isfinite(s)) bad |= CODA_B200_FLAG_NONFINITE_PI;
     const float den = fmaxf(s, 1e-12f);                             // coda.py:230 clamp_(min=1e-12)
+    const float rden = 1.0f / den;
 #pragma unroll
-    for (int k = 0; k < KC; ++k) racc[k] += to_fx(u[r][k] / den, fxs);
+    for (int k = 0; k < KC; ++k) racc[k] += to_fx(row_quot(u[r][k], den, rden), fxs);
   }
 }
 
@@ -984,8 +986,9 @@ __global__ void __launch_bounds__(R1X_THREADS, 1) k_pi_rank1_tma(const float* __
         s = warp_sum(s);
         if (!isfinite(s)) bad |= CODA_B200_FLAG_NONFINITE_PI;
         const float den = fmaxf(s, 1e-12f);                             // coda.py:230 clamp_(min=1e-12)
+        const float rden = 1.0f / den;
 #pragma unroll
-        for (int k = 0; k < KC; ++k) racc[k] += to_fx(u[i][k] / den, fxs);
+        for (int k = 0; k < KC; ++k) racc[k] += to_fx(row_quot(u[i][k], den, rden), fxs);
       }
     }
     __syncwarp();

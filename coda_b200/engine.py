@@ -125,6 +125,7 @@ class Engine:
         self.xchg = None                                      # set by the group (dist.py) before the first exchange
         self._mailbox = None
         self._pi_tc, self._pi_scratch = None, None           # tensor-core marginal pass: decided on first use
+        self.cidx = None                                      # compact slab: inverted index (see _build_compact_index)
         self.stream = torch.cuda.Stream(device=self.dev) if own_stream else None
         self.side = torch.cuda.Stream(device=self.dev)
         self.ev_fork, self.ev_join, self.ev_tables = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
@@ -283,6 +284,7 @@ class Engine:
                            _ptr(self.hard), _ptr(self.pseudo), _ptr(self.disagree), _ptr(self.ens), _ptr(self.flags), s)
                 self._call("coda_b200_confusion_compact", _ptr(cs.ids), _ptr(cs.probs), self.model_stride,
                            _ptr(self.pseudo), H, N, C, self.K, self.fx_shift, _ptr(self.conf_fx), _ptr(self.conf_rest), s)
+                self._build_compact_index()
                 return
             self._call("coda_b200_scan_slab", _ptr(self.preds), self.model_stride, H, N, C, _ptr(self.hard),
                        _ptr(self.pseudo), _ptr(self.disagree), _ptr(self.ens), _ptr(self.flags), s)
@@ -318,6 +320,34 @@ class Engine:
     def construct_finish(self):
         with self._on():
             self.check_flags(sync=True)
+
+    def _build_compact_index(self):
+        """Inverted index of the compact slab (csrc/compact.cu): per (model, class) the items whose top-K list holds the
+        class.  With it the rank-1 marginal refresh reads H short lists (N K / C entries each) instead of the whole slab
+        every step.  Same bytes as the slab (8 per entry): skipped when they do not fit (``CODA_B200_COMPACT_INDEX=0``
+        forces the slab scan)."""
+        self.cidx = None
+        if os.environ.get("CODA_B200_COMPACT_INDEX", "1") == "0":
+            return
+        H, N, C, K, s = self.H, self.N, self.C, self.K, self._s()
+        need = 8 * H * N * K + 16 * (H * C + 1) + 12 * N
+        free, _total = torch.cuda.mem_get_info(self.dev)
+        # leave room for what construction allocates after this point: U, the row cache (bounded by 4 * N * C * Hp bytes
+        # only in the worst case; a quarter of free memory is kept back instead)
+        if need > 0.5 * free:
+            return
+        cs = self.compact
+        counts = self._z((H * C,), torch.int64)
+        self._call("coda_b200_compact_index_count", _ptr(cs.ids), self.model_stride, H, N, C, K, _ptr(counts), s)
+        off = self._z((H * C + 1,), torch.int64)
+        torch.cumsum(counts, 0, out=off[1:])                          # construction-time plumbing
+        cursor = off[:-1].clone()
+        ent = self._e((H * N * K,), torch.int64)                      # {item u32, float bits} pairs
+        rest = self._e((N,), torch.float32)
+        self._call("coda_b200_compact_index_fill", _ptr(cs.ids), _ptr(cs.probs), self.model_stride, H, N, C, K,
+                   _ptr(cursor), _ptr(ent), _ptr(rest), s, n=2)
+        del counts, cursor
+        self.cidx = dict(off=off, ent=ent, rest=rest, delta=self._z((N,), torch.int64))
 
     def _marginals_full(self):
         """coda.py:226-233 as one streaming pass; leaves THIS shard's column sums in ``pisum``."""
@@ -544,7 +574,12 @@ class Engine:
                 self._pair_rows(0, self.max_cls_tiles, gains=False, sel=True)
             if fork:
                 self.ev_join.record(self.side)
-        if self.compact is not None:
+        if self.compact is not None and self.cidx is not None:
+            ix = self.cidx
+            self._call("coda_b200_pi_rank1_index", _ptr(ix["off"]), _ptr(ix["ent"]), _ptr(ix["rest"]), _ptr(self.jvec), H, N, C,
+                       _ptr(self.sel), self.lr, self.fx_shift, _ptr(self.terms), _ptr(ix["delta"]), _ptr(self.U),
+                       _ptr(self.pisum), _ptr(self.flags), s, n=2)
+        elif self.compact is not None:
             cs = self.compact
             self._call("coda_b200_pi_rank1_compact", _ptr(cs.ids), _ptr(cs.probs), self.model_stride, _ptr(self.ens), H, N,
                        C, self.K, _ptr(self.sel), self.lr, self.fx_shift, _ptr(self.terms), _ptr(self.U),
@@ -830,7 +865,7 @@ class Engine:
             self._mailbox.close()
             self._mailbox = None
         for k, v in list(self.__dict__.items()):
-            if isinstance(v, torch.Tensor) or k in ("preds", "compact", "st", "xchg", "_labels_keep"):
+            if isinstance(v, torch.Tensor) or k in ("preds", "compact", "st", "xchg", "_labels_keep", "cidx"):
                 setattr(self, k, None)
 
 

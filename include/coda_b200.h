@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define CODA_B200_VERSION 201
+#define CODA_B200_VERSION 202
 #define CODA_B200_NODES 256 /* quadrature nodes, coda/coda.py:79 */
 #define CODA_B200_MAX_WORLD 16
 #define CODA_B200_REC_WORDS 8 /* arg-max record: {bits vA, iA, cntA, bits vB, iB, bits v2A, bits v2B, 0} */
@@ -173,6 +173,22 @@ int coda_b200_pi_rank1_compact(const uint16_t* ids, const float* probs, int64_t 
                                int64_t N, int C, int K, const int64_t* sel, double lr, int fx_shift,
                                const int32_t* terms, float* U, int64_t* pisum_fx, uint32_t* flags,
                                coda_stream_t stream);
+
+/* Inverted index of the compact slab: for every (model, class) the items whose top-K list holds the class, as
+ * {item u32, float bits of (probs - rest)} pairs.  count: counts[h][c] (ACCUMULATED into, int64); the caller turns
+ * them into offsets [H*C + 1] (exclusive prefix sums) and a cursor copy; fill: places the 8-byte entries (order
+ * inside a list is not defined) and writes rest_sum[n] = sum_h rest(h, n).  N < 2^32 per shard. */
+int coda_b200_compact_index_count(const uint16_t* ids, int64_t model_stride, int H, int64_t N, int C, int K,
+                                  int64_t* counts, coda_stream_t stream);
+int coda_b200_compact_index_fill(const uint16_t* ids, const float* probs, int64_t model_stride, int H, int64_t N, int C,
+                                 int K, int64_t* cursor, void* entries, float* rest_sum, coda_stream_t stream);
+/* coda.py:319 from the index:  sum_h preds[h][n][jvec[h]] = rest_sum[n] + sum over the H lists (h, jvec[h]) of
+ * (probs - rest), scattered into delta [N] (int64 fixed point, zero on entry and on exit: order-independent sums),
+ * then the U row pass of coda_b200_pi_rank1.  Reads H lists of about N K / C entries instead of the whole slab.
+ * `terms` is only consulted for "no label applied in this step" ({0, -1}). */
+int coda_b200_pi_rank1_index(const int64_t* offsets, const void* entries, const float* rest_sum, const int32_t* jvec,
+                             int H, int64_t N, int C, const int64_t* sel, double lr, int fx_shift, const int32_t* terms,
+                             int64_t* delta, float* U, int64_t* pisum_fx, uint32_t* flags, coda_stream_t stream);
 
 /* ---- Beta quadrature tables (dirichlet_to_beta coda.py:14-25, compute_pbest_beta_batched
  *      coda.py:77-119, batch_update_beta coda.py:150-168) for classes [cls_lo, cls_hi) ------- */

@@ -80,3 +80,41 @@ def test_compact_slab_shards_and_device_loop():
     if not ora.stochastic:                                   # no isclose tie on the way: arg-max is the reference's rule
         assert one.history()[0].tolist() == picks
         np.testing.assert_allclose(one.get_pbest().cpu().numpy(), ora.get_pbest().numpy(), atol=1e-5)
+
+
+@pytest.mark.parametrize("shape", [(24, 1500, 30, 4, 11), (17, 3000, 300, 3, 2)])
+def test_inverted_index_refresh_equals_the_slab_scan(shape, monkeypatch):
+    """The rank-1 marginal refresh from the inverted index (H short lists, int64 fixed-point scatter) against the kernel that
+    scans the whole compact slab: same picks, marginals within fp32 rounding, and the index path itself bit-identical for
+    1 and 3 shards; the scatter target is back to zero after every step."""
+    from coda_b200 import CODA, CompactDataset
+    H, N, C, K, seed = shape
+    slab, _dense, labels = _case(H, N, C, K, seed)
+    dev = torch.device("cuda:0")
+    monkeypatch.setenv("CODA_B200_COMPACT_INDEX", "0")
+    scan = CODA(CompactDataset(slab.to(dev), labels.to(dev)))
+    assert scan.engine.cidx is None
+    monkeypatch.setenv("CODA_B200_COMPACT_INDEX", "1")
+    idx = CODA(CompactDataset(slab.to(dev), labels.to(dev)))
+    many = CODA(CompactDataset(slab.to(dev), labels.to(dev)), shards=3)
+    ix = idx.engine.cidx
+    assert ix is not None and int(ix["off"][-1]) == int((slab.ids < C).sum())
+    for step in range(5):
+        random.seed(step)
+        i, q = idx.get_next_item_to_label()
+        random.seed(step)
+        k, _ = many.get_next_item_to_label()
+        assert i == k, step                                   # bit-identical state: same scores, same tie draw
+        scan.get_next_item_to_label()
+        assert float(scan._cat("eig")[i]) >= scan.last_report["best_val"] - 1e-6   # the scan path scores the same item (near-)best
+        for s in (idx, scan, many):
+            s.add_label(i, int(labels[i]), q)
+        torch.cuda.synchronize()
+        np.testing.assert_allclose(idx.engine.U.cpu().numpy(), scan.engine.U.cpu().numpy(), rtol=2e-6)
+        np.testing.assert_allclose(idx.pi_hat.cpu().numpy(), scan.pi_hat.cpu().numpy(), rtol=1e-6)
+        assert torch.equal(idx.pi_hat, many.pi_hat) and torch.equal(idx.dirichlets, many.dirichlets)
+        assert int(ix["delta"].abs().max()) == 0
+    idx.run_steps(4, labels)
+    many.run_steps(4, labels)
+    assert idx.history()[0].tolist() == many.history()[0].tolist()
+    assert torch.equal(idx.pi_hat, many.pi_hat)

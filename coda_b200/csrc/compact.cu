@@ -345,16 +345,21 @@ __global__ void __launch_bounds__(256) k_pi_rank1_compact(const uint16_t* __rest
         constexpr int KR = KCU > 0 ? KCU : 1;
         float u[KR];
         float s = 0.f;
+        // every load of the row before the one store into it: a store between them orders the later loads behind it
+        // (possible alias) and the row costs KR dependent memory round trips instead of one (ncu: 15 us per row)
 #pragma unroll
         for (int k = 0; k < KR; ++k) {
           const int c = lane + 32 * k;
           u[k] = c < C ? urow[c] : 0.f;
-          if (c == t) {
-            u[k] += dr;
-            urow[c] = u[k];
-          }
+        }
+#pragma unroll
+        for (int k = 0; k < KR; ++k) {
+          if (lane + 32 * k == t) u[k] += dr;
           s += u[k];
         }
+#pragma unroll
+        for (int k = 0; k < KR; ++k)
+          if (lane + 32 * k == t) urow[t] = u[k];
         s = warp_sum(s);
         if (!isfinite(s)) bad |= CODA_B200_FLAG_NONFINITE_PI;
         const float den = fmaxf(s, 1e-12f);                             // coda.py:230 clamp_(min=1e-12)
@@ -363,15 +368,16 @@ __global__ void __launch_bounds__(256) k_pi_rank1_compact(const uint16_t* __rest
         for (int k = 0; k < KR; ++k) racc[k] += to_fx(row_quot(u[k], den, rden), fxs);
         continue;
       }
-      float s = 0.f;
-      for (int c = lane; c < C; c += 32) {
+      float s = 0.f, ut = 0.f;
+      for (int c = lane; c < C; c += 32) {      // loads only (see above); column t is stored afterwards by its lane
         float u = urow[c];
         if (c == t) {
           u += dr;
-          urow[c] = u;
+          ut = u;
         }
         s += u;
       }
+      if (lane == (t & 31)) urow[t] = ut;
       s = warp_sum(s);
       if (!isfinite(s)) bad |= CODA_B200_FLAG_NONFINITE_PI;
       const float den = fmaxf(s, 1e-12f);                               // coda.py:230 clamp_(min=1e-12)
@@ -596,16 +602,21 @@ __global__ void __launch_bounds__(256) k_r1i_rows(const float* __restrict__ R, u
         constexpr int KR = KCU > 0 ? KCU : 1;
         float u[KR];
         float s = 0.f;
+        // every load of the row before the one store into it: a store between them orders the later loads behind it
+        // (possible alias) and the row costs KR dependent memory round trips instead of one (ncu: 15 us per row)
 #pragma unroll
         for (int k = 0; k < KR; ++k) {
           const int c = lane + 32 * k;
           u[k] = c < C ? urow[c] : 0.f;
-          if (c == t) {
-            u[k] += dr;
-            urow[c] = u[k];
-          }
+        }
+#pragma unroll
+        for (int k = 0; k < KR; ++k) {
+          if (lane + 32 * k == t) u[k] += dr;
           s += u[k];
         }
+#pragma unroll
+        for (int k = 0; k < KR; ++k)
+          if (lane + 32 * k == t) urow[t] = u[k];
         s = warp_sum(s);
         if (!isfinite(s)) bad |= CODA_B200_FLAG_NONFINITE_PI;
         const float den = fmaxf(s, 1e-12f);                             // coda.py:230 clamp_(min=1e-12)
@@ -614,15 +625,16 @@ __global__ void __launch_bounds__(256) k_r1i_rows(const float* __restrict__ R, u
         for (int k = 0; k < KR; ++k) racc[k] += to_fx(row_quot(u[k], den, rden), fxs);
         continue;
       }
-      float s = 0.f;
-      for (int c = lane; c < C; c += 32) {
+      float s = 0.f, ut = 0.f;
+      for (int c = lane; c < C; c += 32) {      // loads only (see above); column t is stored afterwards by its lane
         float u = urow[c];
         if (c == t) {
           u += dr;
-          urow[c] = u;
+          ut = u;
         }
         s += u;
       }
+      if (lane == (t & 31)) urow[t] = ut;
       s = warp_sum(s);
       if (!isfinite(s)) bad |= CODA_B200_FLAG_NONFINITE_PI;
       const float den = fmaxf(s, 1e-12f);                               // coda.py:230 clamp_(min=1e-12)

@@ -502,15 +502,16 @@ extern "C" int coda_b200_pi_full(const float* preds, int64_t model_stride, const
 __device__ __forceinline__ void row_accumulate(float* __restrict__ urow, int C, int lane, float fxs, int t,
                                                float delta_t, float* __restrict__ xi_out,
                                                long long* __restrict__ wacc, uint32_t& bad) {
-  float s = 0.f;
-  for (int c = lane; c < C; c += 32) {
-    float u = urow[c];
+  float s = 0.f, ut = 0.f;
+  for (int c = lane; c < C; c += 32) {      // loads only: a store inside this loop would order every later load behind it
+    float u = urow[c];                       // (possible alias) and turn the row into C / 32 dependent round trips
     if (c == t) {
       u += delta_t;
-      urow[c] = u;
+      ut = u;
     }
     s += u;
   }
+  if (t >= 0 && lane == (t & 31)) urow[t] = ut;
   s = warp_sum(s);
   if (!isfinite(s)) bad |= CODA_B200_FLAG_NONFINITE_PI;
   const float den = fmaxf(s, 1e-12f);                               // coda.py:230 clamp_(min=1e-12)
